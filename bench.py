@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — CarEnv env-steps/sec (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repository's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[3] — tracks/big_track.json, 1,048,576
+environments in total, i.i.d. uniform random actions, sharded over the N ranks by contiguous env
+ranges with no data-path collective (strong scaling: the total is fixed).  One timed "step" is one
+`carenv_rollout` launch per rank that advances every local environment by `chunk` CarEnv steps and
+writes the observation, reward and both flags of every one of them to HBM.
+
+  value     env-steps/s with actions already resident in HBM (device timed, CUDA events, max over ranks)
+  e2e       env-steps/s through the reference-facing API VecCarEnv.step(numpy actions) -> numpy
+            results: host->device copy of the actions and device->host copy of obs/reward/flags/info
+            from/to pinned memory inside the timed region, every step
+  roofline  the step kernel against the FP32 pipe (5,286 algorithmic flop per env-step on
+            big_track; nominal peak 148 SM x 128 lanes x 2 x sm_max_mhz, and an FFMA probe measured in
+            the same run) plus its algorithmic HBM bytes against MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (a Python restatement of lib/car_env.py, bit-exact against the
+            reference's golden trajectories) on the host cores, on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TOTAL_ENVS = 1_048_576
+TRACK = "big_track"
+N_SEG = 24
+FLOP_PER_ENV_STEP = 18 * (12 * N_SEG + 4) + 30          # 5,286
+# algorithmic bytes per env-step of the rollout launch (state stays in registers between steps):
+# action u8 1 + obs 72 + reward 4 + term 1 + trunc 1; the 48 B state is read and written once per launch
+BYTES_PER_ENV_STEP = 1 + 72 + 4 + 1 + 1
+STATE_BYTES = 48
+METRIC = "CarEnv env-steps/sec"
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+_W_ENV = None
+
+
+def _w_init(track_path):
+    global _W_ENV
+    sys.path.insert(0, ROOT)
+    from oracle.carenv_port import PortCarEnv
+
+    _W_ENV = PortCarEnv(track_path)
+    _W_ENV.reset()
+
+
+def _w_run(args):
+    seed, n_steps = args
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    acts = rng.integers(0, 9, size=n_steps)
+    env = _W_ENV
+    for a in acts:
+        _, _, te, tr, _ = env.step(int(a))
+        if te or tr:
+            env.reset()                       # same-step autoreset
+    return n_steps
+
+
+class CpuPortPool:
+    """The reference's CPU path as restated by oracle/carenv_port.py, one process per host core."""
+
+    def __init__(self, track_path, cores=None):
+        import multiprocessing as mp
+
+        self.cores = cores or min(os.cpu_count() or 1, 128)
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_w_init, initargs=(track_path,))
+        self.seed = 0
+
+    def run(self, steps_per_env):
+        t0 = time.perf_counter()
+        tasks = [(self.seed + i, steps_per_env) for i in range(self.cores)]
+        self.seed += self.cores
+        done = sum(self.pool.map(_w_run, tasks, chunksize=1))
+        return done, time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_baseline(track_path, target_seconds=12.0):
+    pool = CpuPortPool(track_path)
+    try:
+        pool.run(16)                                           # warm-up / calibration
+        n, dt = pool.run(64)
+        per_env = max(64, int(64 * target_seconds / max(dt, 1e-3)))
+        n, dt = pool.run(per_env)
+    finally:
+        pool.close()
+    return {"value": n / dt, "unit": "env-steps/s", "cores": pool.cores, "kind": "port",
+            "sample": f"{pool.cores} envs x {per_env} steps, big_track.json, uniform random actions, "
+                      f"oracle/carenv_port.py (Python restatement of lib/car_env.py), one process per core, {dt:.1f} s"}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import ppo_car_b200.track as trk
+
+    path = trk.builtin_track(TRACK)
+    pool = CpuPortPool(path)
+    per_env = 96                                             # env-steps per worker per timed "step"
+    try:
+        for _ in range(max(args.warmup, 1)):
+            pool.run(per_env)
+        n_tot, t_tot = 0, 0.0
+        for _ in range(args.steps):
+            n, dt = pool.run(per_env)
+            n_tot += n
+            t_tot += dt
+    finally:
+        pool.close()
+    val = n_tot / t_tot
+    sample = (f"{pool.cores} envs x {per_env} env-steps per step, big_track.json, uniform random actions, "
+              "oracle/carenv_port.py (Python restatement of lib/car_env.py; the reference is pure Python and "
+              "cannot travel to the GPU box), one process per host core")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"tracks/{TRACK}.json, uniform random actions, same-step autoreset; "
+                                   f"bounded sample of the {TOTAL_ENVS}-env workload: {sample}"},
+            "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": pool.cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import ppo_car_b200
+    from ppo_car_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path for --impl ours)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from ppo_car_b200.shard import shard_range
+
+    total = args.envs
+    lo, hi = shard_range(total, world, rank)
+    n = hi - lo
+    chunk = args.chunk
+    track = ppo_car_b200.builtin_track(TRACK)
+    env = ppo_car_b200.VecCarEnv(n, track, device=dev, with_info=True)
+    env.reset()
+    # actions: shard-count-invariant stream (global env id decides the column), two alternating chunks
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    n_act_bufs = 2
+    acts = [torch.randint(0, 9, (chunk, total), generator=gen, device=dev, dtype=torch.uint8)[:, lo:hi].contiguous()
+            for _ in range(n_act_bufs)]
+    obs = torch.empty((chunk, n, 18), dtype=torch.float32, device=dev)
+    rew = torch.empty((chunk, n), dtype=torch.float32, device=dev)
+    term = torch.empty((chunk, n), dtype=torch.uint8, device=dev)
+    trunc = torch.empty((chunk, n), dtype=torch.uint8, device=dev)
+
+    def one_step(i):
+        env.rollout(acts[i % n_act_bufs], obs_out=obs, reward_out=rew, term_out=term, trunc_out=trunc)
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    evs[0].record()
+    for i in range(args.steps):
+        one_step(i)
+        evs[i + 1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    dev_ms = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = args.steps * chunk * total / (dev_ms_max * 1e-3)
+    slow = env.slow_path_counts()
+
+    # ---- e2e: reference-facing API with HOST buffers (numpy in, numpy out), one env step per call
+    e_steps = args.e2e_steps
+    rng = np.random.default_rng(99 + rank)
+    host_actions = [rng.integers(0, 9, size=n).astype(np.int64) for _ in range(4)]   # int64: what train.py:185 passes
+    for i in range(2):
+        env.step(host_actions[i % 4])
+    barrier()
+    t0 = time.perf_counter()
+    sink = 0.0
+    for i in range(e_steps):
+        o, r, te, tr, info = env.step(host_actions[i % 4])
+        sink += float(r[0])                       # the result is on the host (pinned buffer) when step() returns
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te2e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
+    e2e_value = e_steps * total / float(te2e.item())
+    h2d = total * 1                               # uint8 actions (cast on the host before the copy)
+    d2h = total * (72 + 4 + 1 + 1 + 16)
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        sm_max = float(clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0))
+        fp32_nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        # FFMA probe, timed alone on this GPU
+        L = _lib.lib()
+        import ctypes as C
+
+        scratch = torch.zeros(4, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        blocks, iters = 148 * 8, 20000
+        L.carenv_bench_ffma(blocks, 1000, C.c_void_p(scratch.data_ptr()), st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.carenv_bench_ffma(blocks, iters, C.c_void_p(scratch.data_ptr()), st)
+        e1.record()
+        torch.cuda.synchronize()
+        ffma_tflops = blocks * 256 * iters * 64 * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+        launch_ms = sum(per_launch_ms) / len(per_launch_ms)      # rank 0's average launch duration
+        steps_per_launch = chunk * n
+        achieved_tflops = steps_per_launch * FLOP_PER_ENV_STEP / (launch_ms * 1e-3) / 1e12
+        bytes_per_launch = steps_per_launch * BYTES_PER_ENV_STEP + n * 2 * STATE_BYTES
+        achieved_gbs = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+        cpu = cpu_baseline(track) if not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 ray casting, f64 state", "data": "synthetic",
+            "config": {"workload": f"tracks/{TRACK}.json, {total} envs total ({n} per GPU), uniform random actions "
+                                   f"resident in HBM, same-step autoreset, {chunk} env steps per launch; every step "
+                                   "writes obs[18] f32 + reward f32 + terminated/truncated u8 per env",
+                       "envs_total": total, "envs_per_gpu": n, "steps_per_launch": chunk, "sharding": f"env{world}",
+                       "cache": f"outputs per launch {obs.numel() * 4 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},
+            "wall_s": t_wall,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "VecCarEnv.step(numpy int64 actions) -> numpy obs/reward/terminated/truncated/info",
+                    "steps": e_steps},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_nominal, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / fp32_nominal, "traffic": None,
+                         "kernel": "k_rollout<uint8,uint8>", "launch_ms": launch_ms,
+                         "flop_per_env_step": FLOP_PER_ENV_STEP,
+                         "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no "
+                                        "FP32 entry)",
+                         "ffma_probe_tflops": ffma_tflops, "frac_of_ffma_probe": achieved_tflops / ffma_tflops},
+            "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved_gbs / hbm_peak, "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                             "peak_source": hbm_src},
+            "slow_path": {k: v for k, v in slow.items()},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=TOTAL_ENVS, help="total environments over all GPUs")
+    ap.add_argument("--chunk", type=int, default=16, help="env steps per rollout launch")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

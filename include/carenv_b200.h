@@ -1,0 +1,116 @@
+/* carenv_b200.h — C ABI of libcarenv_b200.so (B200 / sm_100a).
+ *
+ * The drop-in boundary for the one hot path of ProfessorNova/PPO-Car that this repository
+ * accelerates: the batched CarEnv step with same-step autoreset and the GAE reverse scan.
+ * The reference has no FFI layer (it is pure Python); each entry point below names the
+ * reference interface it stands in for (file:line in the reference tree).  INTEGRATION.md
+ * shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative code on failure
+ *     (CARENV_E_* below, or -1000 - cudaError_t for CUDA failures); no exception or abort
+ *     crosses the boundary; carenv_last_error() returns a thread-local message.
+ *   - all pointers except `handle` and the *_host arguments are DEVICE pointers owned by
+ *     the caller (PyTorch tensors); they are borrowed for the duration of the enqueued
+ *     kernel.  The library owns only the opaque handle and its small geometry tables.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *     all work is enqueued on it and the call returns without synchronising.
+ *   - there is no CPU implementation behind this interface.
+ *
+ * Environment state (structure of arrays, one element per environment):
+ *   pos  double[N][2]   x, y in pixels                     (Car.__pos,      lib/car_env.py:245)
+ *   vel  double[N][2]   vx, vy in pixels/step              (Car.__velocity, lib/car_env.py:262)
+ *   ints int32 [N][4]   heading index k (rotation = initial_angle + 5k degrees, k mod 72),
+ *                       time_step, next_gate_index, passed_reward_gates
+ *                                                          (lib/car_env.py:247, 490, 494-496)
+ */
+#ifndef CARENV_B200_H
+#define CARENV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CARENV_ABI_VERSION 1
+#define CARENV_OBS_DIM 18      /* 6 + num_rays, lib/car_env.py:513-519 */
+#define CARENV_NUM_ACTIONS 9   /* spaces.Discrete(9), lib/car_env.py:525 */
+#define CARENV_MAX_SEGMENTS 128
+
+#define CARENV_E_INVAL (-1)    /* bad argument (null pointer, size, dtype) */
+#define CARENV_E_TRACK (-2)    /* track does not fit (too many segments) or is malformed */
+#define CARENV_E_NOGPU (-3)    /* no usable CUDA device */
+
+/* action element type of the `actions` argument */
+#define CARENV_ACT_U8 0
+#define CARENV_ACT_I32 1
+#define CARENV_ACT_I64 2       /* what Categorical.sample() yields, lib/model.py:38 */
+
+/* element type of the terminated / truncated outputs */
+#define CARENV_FLAG_U8 0
+#define CARENV_FLAG_F32 1      /* what lib/buffer.py:16-17 stores */
+
+int carenv_abi_version(void);
+const char *carenv_last_error(void);
+
+/* Build the per-track tables on `device`.
+ * Stands in for CarEnv.__init__ + CarEnv.load_track + the geometry rebuild in CarEnv.reset
+ * (lib/car_env.py:475-533, 535-567, 638-676).  Coordinates are already in pixels (x*1280,
+ * y*720); walls are [n_walls][4] = x1 y1 x2 y2, outer polyline first then inner, in the
+ * reference's order; gates are [n_gates][4] from consecutive point pairs. */
+int carenv_create(const double *walls_xyxy_host, int n_walls, const double *gates_xyxy_host, int n_gates,
+                  double init_x, double init_y, double init_angle_deg, int device, void **handle);
+int carenv_destroy(void *handle);
+
+/* The observation CarEnv.reset returns (a constant of the track; lib/car_env.py:682-691). */
+int carenv_reset_obs(void *handle, float *obs18_host);
+
+/* CarEnv.reset for n_envs environments (lib/car_env.py:605-691): start pose, zero velocity,
+ * counters cleared; obs_out [n_envs][18] float32 (may be NULL). */
+int carenv_reset(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, float *obs_out, void *stream);
+
+/* One CarEnv.step for every environment, with the same-step autoreset of
+ * gymnasium.vector.AsyncVectorEnv (lib/car_env.py:693-760; train.py:138,185).
+ *   actions     [n_envs] of action_dtype, values 0..8
+ *   reward_scale            TransformReward factor (train.py:65,68); reward_out = float32(r * scale)
+ *   obs_out     [n_envs][18] float32; the RESET observation where the episode ended
+ *   reward_out  [n_envs] float32
+ *   term_out / trunc_out [n_envs] of flag_dtype
+ *   info_out    [n_envs][4] int32 or NULL: gates_passed, time_passed (info dict of the finished
+ *               step, lib/car_env.py:599-603), next_gate_index, bit0 = gate hit, bit1 = lap */
+int carenv_step(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions,
+                int action_dtype, double reward_scale, float *obs_out, float *reward_out, void *term_out,
+                void *trunc_out, int flag_dtype, int32_t *info_out, void *stream);
+
+/* n_steps consecutive steps in ONE launch (the rollout loop of train.py:173-195 with the
+ * actions given up front).  actions is [n_steps][n_envs]; every output is [n_steps][n_envs]...
+ * with the same element layouts as carenv_step; obs_out, info_out may be NULL.  The state
+ * arrays hold the final state on completion. */
+int carenv_rollout(void *handle, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints,
+                   const void *actions, int action_dtype, double reward_scale, float *obs_out, float *reward_out,
+                   void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream);
+
+/* Slow-path counters since the last reset of the counters: [0] lines re-evaluated in float64
+ * because an endpoint was within eps of a ray line, [1] rays re-evaluated because a cardinal
+ * distance was within the band around 10 px, [2] gate tests re-evaluated, [3] distances below
+ * the tiny threshold.  Synchronises the device. */
+int carenv_stats(void *handle, unsigned long long out4_host[4], int reset_counters);
+
+/* Buffer.calculate_advantages (lib/buffer.py:36-64): float32 GAE(lambda) reverse scan in the
+ * reference's own operation order, every operation individually rounded.
+ *   rew, val, term, trunc   [T][N] float32 (the Buffer layout, lib/buffer.py:14-17)
+ *   last_val, last_term, last_trunc [N] float32
+ *   adv, ret                [T][N] float32 outputs (ret = adv + val) */
+int gae_reverse_scan(const float *rew, const float *val, const float *term, const float *trunc,
+                     const float *last_val, const float *last_term, const float *last_trunc, float *adv, float *ret,
+                     int T, int N, double gamma, double gae_lambda, void *stream);
+
+/* Measurement helper (no reference counterpart): an FFMA-only kernel, blocks x 256 threads x
+ * iters x 64 FFMA, used by bench.py to measure the FP32-pipe peak the step kernel is compared with. */
+int carenv_bench_ffma(int blocks, int iters, float *scratch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARENV_B200_H */

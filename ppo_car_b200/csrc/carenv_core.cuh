@@ -1,0 +1,361 @@
+// carenv_core.cuh — per-environment arithmetic of the batched CarEnv step (sm_100a).
+//
+// One thread owns one environment.  Everything here is __host__ __device__ so that the
+// very same arithmetic can be compiled for the host by tests/host_emul (a TEST harness
+// that replays the kernel's decisions on the CPU against the float64 oracle); the product
+// library only ever runs it on the GPU.
+//
+// What it computes (reference: /root/reference/lib/car_env.py):
+//   decode_action      698-722   Discrete(9) -> thrust sign, turn sign, +0.01 bonus
+//   gate_touched       394-408, 376-392, 725-726  test of the NEXT gate with the cardinal
+//                                rays of the pose left by the previous update
+//   integrate          444-461   vel += acc; friction iff no thrust; per-axis clip; pos += vel
+//   cast_walls         155-213, 360-392, 463-469  12 ray distances + wall collision
+//   step               693-760   reward schedule, flags, truncation, observation, autoreset
+//
+// Numerical design:
+//   * pos/vel are float64 and integrated with the reference's operations in the
+//     reference's order (no FMA contraction), so trajectories follow the float64 oracle.
+//   * heading = initial_angle + 5*k degrees; all trigonometry is a 72-entry table.
+//   * ray casting is float32 on the FMA pipe.  The 12 rays lie on 6 lines through the car
+//     (ray i and ray i+6 are opposite), so each wall segment is tested once per LINE:
+//       q(P)   = cross(P - pos, d)            signed offset of an endpoint from the line
+//       hit   <=> q(A), q(B) have opposite signs            (== 0 < t < 1 of Ray.cast)
+//       u      = cross(e, A - pos) / cross(e, d)            (== u of Ray.cast, = distance)
+//     and the per-ray minimum distance is kept as the maximum of r = 1/u per sign.
+//   * every decision that feeds an integer output (hit/miss, d < 10) is taken in float32
+//     only when it is outside a guard band that bounds the float32 error; inside the band
+//     the ray is re-evaluated with the reference's literal float64 formulas
+//     (exact_ray_distance).  Integer outputs therefore follow the float64 oracle.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CE_HD __host__ __device__ __forceinline__
+#define CE_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define CE_HD inline
+#define CE_HD_NOINLINE
+#endif
+
+namespace carenv {
+
+constexpr int kNumRays = 12;
+constexpr int kObsDim = 18;
+constexpr int kHeadings = 72;      // 360 / 5 degrees
+constexpr int kMaxSeg = 128;       // wall segments carried in kernel-parameter space
+constexpr int kTimeLimit = 1000;   // lib/car_env.py:491
+
+struct F2 { float x, y; };
+struct D2 { double x, y; };
+
+// One wall segment A->B.  Endpoints are split hi+lo so that (P - pos) can be formed in
+// float32 with a relative (not absolute) rounding error.
+struct SegF {
+    float ahx, ahy, alx, aly;
+    float bhx, bhy, blx, bly;
+    float ex, ey;          // B - A rounded from float64
+    int chain_start;       // 1: A is not the previous segment's B
+    int pad;
+};
+struct SegD { double K, ex, ey; };   // K = cross(e, A):  cross(e, A - pos) = K - (ex*py - ey*px)
+
+struct GateRec { double x1, y1, x2, y2; float ex, ey, len, pad; };
+
+struct TrackParams {
+    int n_seg, n_gates, start_destroyed, pad0;
+    float eps_q;        // |q| below this: hit/miss undecidable in float32
+    float coll_band;    // relative half-width of the band around d == 10
+    float tiny_d;       // distances below this are re-evaluated (sign of u uncertain)
+    float gate_band;    // gate margin band, in units of the gate length
+    double start_x, start_y;
+    float reset_obs[kObsDim];
+    float pad1[2];
+    SegF segf[kMaxSeg];
+    SegD segd[kMaxSeg];
+};
+
+// Small tables that are indexed per thread (heading, gate index): global memory on the
+// host side of the handle, staged to shared memory by the kernels.
+struct Tables {
+    const F2 *trig32;        // [72] (cos, sin) of radians(initial_angle + 5k), float32
+    const D2 *trig64;        // [72] same, float64
+    const D2 *acc64;         // [72] (cos*0.8, sin*0.8), float64  (lib/car_env.py:430)
+    const GateRec *gates;    // [n_gates]
+    const double *walls64;   // [n_seg][4] x1 y1 x2 y2 — only read on the exact path
+};
+
+struct EnvState {
+    double px, py, vx, vy;
+    int k;          // heading index, rotation = initial_angle + 5k (mod 72)
+    int t;          // time_step
+    int next_gate;  // next_gate_index
+    int passed;     // passed_reward_gates (cumulative over laps)
+};
+
+struct StepResult {
+    float obs[kObsDim];
+    float reward;       // float32(reward_f64 * reward_scale)
+    int terminated, truncated;
+    int gates_passed, time_passed, next_gate;   // info of the finished step (pre-reset)
+    int gate_hit, lap;
+};
+
+// slow-path counters (optional)
+enum { kStatLine = 0, kStatBand = 1, kStatGate = 2, kStatTiny = 3, kNumStats = 4 };
+
+// ---- individually rounded arithmetic (never contracted, identical on host and device) ----
+#if defined(__CUDA_ARCH__)
+CE_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+CE_HD double dsub(double a, double b) { return __dadd_rn(a, -b); }
+CE_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+CE_HD double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+CE_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+CE_HD float fsub(float a, float b) { return __fadd_rn(a, -b); }
+CE_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+CE_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#if defined(CARENV_IEEE_RCP)
+CE_HD float frcp(float x) { return __frcp_rn(x); }
+#else
+CE_HD float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
+CE_HD void stat_add(unsigned long long *s, int i) { if (s) atomicAdd(s + i, 1ULL); }
+#else
+CE_HD double dadd(double a, double b) { return a + b; }   // host build: -ffp-contract=off
+CE_HD double dsub(double a, double b) { return a - b; }
+CE_HD double dmul(double a, double b) { return a * b; }
+CE_HD double dfma(double a, double b, double c) { return fma(a, b, c); }
+CE_HD float fadd(float a, float b) { return a + b; }
+CE_HD float fsub(float a, float b) { return a - b; }
+CE_HD float fmul(float a, float b) { return a * b; }
+CE_HD float ffma(float a, float b, float c) { return fmaf(a, b, c); }
+CE_HD float frcp(float x) { return 1.0f / x; }
+CE_HD void stat_add(unsigned long long *s, int i) { if (s) __atomic_fetch_add(s + i, 1ULL, __ATOMIC_RELAXED); }
+#endif
+
+CE_HD int wrap72(int k) { return k >= kHeadings ? k - kHeadings : (k < 0 ? k + kHeadings : k); }
+
+// ---- literal float64 evaluation (the reference's formulas, lib/car_env.py:155-213) ----------
+CE_HD bool exact_cast(double ox, double oy, double dx, double dy, const double *seg, double &dist) {
+    const double x1 = seg[0], y1 = seg[1], x2 = seg[2], y2 = seg[3];
+    const double x3 = ox, y3 = oy, x4 = dadd(ox, dx), y4 = dadd(oy, dy);
+    const double den = dsub(dmul(dsub(x1, x2), dsub(y3, y4)), dmul(dsub(y1, y2), dsub(x3, x4)));
+    if (den == 0) return false;
+    const double t = dsub(dmul(dsub(x1, x3), dsub(y3, y4)), dmul(dsub(y1, y3), dsub(x3, x4))) / den;
+    const double u = -dsub(dmul(dsub(x1, x2), dsub(y1, y3)), dmul(dsub(y1, y2), dsub(x1, x3))) / den;
+    if (0 < t && t < 1 && u > 0) {
+        const double hx = dadd(x1, dmul(t, dsub(x2, x1))), hy = dadd(y1, dmul(t, dsub(y2, y1)));
+        const double gx = dsub(ox, hx), gy = dsub(oy, hy);
+        dist = sqrt(dadd(dmul(gx, gx), dmul(gy, gy)));
+        return true;
+    }
+    return false;
+}
+
+CE_HD_NOINLINE double exact_ray_distance(double ox, double oy, double dx, double dy, const double *segs, int n) {
+    double best = 1000.0;
+    for (int j = 0; j < n; ++j) {
+        double d;
+        if (exact_cast(ox, oy, dx, dy, segs + 4 * j, d) && d < best) best = d;
+    }
+    return best;
+}
+
+// ---- action decode (lib/car_env.py:698-722) -------------------------------------------------
+CE_HD void decode_action(int a, int &thrust, int &turn) {
+    thrust = (a == 0 || a == 4 || a == 5) ? 1 : ((a == 1 || a == 6 || a == 7) ? -1 : 0);
+    turn = (a == 3 || a == 5 || a == 7) ? 1 : ((a == 2 || a == 4 || a == 6) ? -1 : 0);
+}
+
+// ---- gate test with the pose left by the previous update (lib/car_env.py:725, 394-408) ------
+// Tests gate `next_gate` only: gates below it are exactly the inactive ones, so the first
+// active gate the reference's ordered scan can return with index == next_gate is this one.
+CE_HD bool gate_touched(const EnvState &s, const TrackParams &P, const Tables &T, unsigned long long *stats) {
+    const GateRec g = T.gates[s.next_gate];
+    const float x1 = (float)dsub(g.x1, s.px), y1 = (float)dsub(g.y1, s.py);
+    const float x2 = (float)dsub(g.x2, s.px), y2 = (float)dsub(g.y2, s.py);
+    const F2 d = T.trig32[s.k];
+    const float un = ffma(g.ex, y1, -fmul(g.ey, x1));            // cross(e, A')
+    const float q1 = ffma(x1, d.y, -fmul(y1, d.x)), q2 = ffma(x2, d.y, -fmul(y2, d.x));   // line of rays 0/6
+    const float p1 = ffma(x1, d.x, fmul(y1, d.y)), p2 = ffma(x2, d.x, fmul(y2, d.y));     // line of rays 3/9
+    const float den0 = ffma(g.ex, d.y, -fmul(g.ey, d.x));
+    const float den3 = ffma(g.ex, d.x, fmul(g.ey, d.y));
+    const float m0 = fsub(fabsf(un), fmul(10.0f, fabsf(den0)));  // < 0  <=>  |u| < 10 on that line
+    const float m3 = fsub(fabsf(un), fmul(10.0f, fabsf(den3)));
+    const bool c0 = fmul(q1, q2) < 0.0f, c3 = fmul(p1, p2) < 0.0f;
+    const float qmin = fminf(fminf(fabsf(q1), fabsf(q2)), fminf(fabsf(p1), fabsf(p2)));
+    const float band = fmul(P.gate_band, g.len);
+    // a line only matters if it is (possibly) crossed; its margin only if it is close to 0
+    const bool unsure = (qmin < P.eps_q) || (c0 && fabsf(m0) < band) || (c3 && fabsf(m3) < band);
+    if (!unsure) return (c0 && m0 < 0.0f) || (c3 && m3 < 0.0f);
+    stat_add(stats, kStatGate);
+    const double seg[4] = {g.x1, g.y1, g.x2, g.y2};
+    for (int r = 0; r < 4; ++r) {
+        const D2 dd = T.trig64[wrap72(s.k + 18 * r)];
+        double dist;
+        if (exact_cast(s.px, s.py, dd.x, dd.y, seg, dist) && dist < 10.0) return true;
+    }
+    return false;
+}
+
+// ---- Car.update without the rays (lib/car_env.py:452-461) -----------------------------------
+CE_HD void integrate(EnvState &s, int thrust, int k_pre, const Tables &T) {
+    if (thrust != 0) {
+        const D2 a = T.acc64[k_pre];
+        s.vx = dadd(s.vx, thrust > 0 ? a.x : -a.x);
+        s.vy = dadd(s.vy, thrust > 0 ? a.y : -a.y);
+    } else {
+        s.vx = dmul(s.vx, 0.8);      // vel + 0 == vel; friction only without thrust (1 - 0.2 == 0.8 in double)
+        s.vy = dmul(s.vy, 0.8);
+    }
+    s.vx = fmin(fmax(s.vx, -10.0), 10.0);
+    s.vy = fmin(fmax(s.vy, -10.0), 10.0);
+    s.px = dadd(s.px, s.vx);
+    s.py = dadd(s.py, s.vy);
+}
+
+// ---- the 12 ray distances and the wall-collision decision -------------------------------------
+// dist[i] (pixels, float32) for ray i = heading + 30*i degrees; returns destroyed.
+CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, float dist[kNumRays],
+                      unsigned long long *stats) {
+    const float phx = (float)s.px, phy = (float)s.py;
+    const float plx = (float)dsub(s.px, (double)phx), ply = (float)dsub(s.py, (double)phy);
+    float c[3], sn[3];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const F2 d = T.trig32[wrap72(s.k + 6 * l)];
+        c[l] = d.x; sn[l] = d.y;
+    }
+    const float R0 = 1.0e-3f;           // 1/1000: "no hit" (lib/car_env.py:198)
+    float Rp[6], Rm[6], gq[6], qa[6];
+#pragma unroll
+    for (int l = 0; l < 6; ++l) { Rp[l] = R0; Rm[l] = -R0; gq[l] = 1.0e30f; qa[l] = 0.0f; }
+
+#pragma unroll 2
+    for (int j = 0; j < P.n_seg; ++j) {
+        const SegF f = P.segf[j];
+        const SegD g = P.segd[j];
+        if (f.chain_start) {
+            const float ax = fadd(fsub(f.ahx, phx), fsub(f.alx, plx));
+            const float ay = fadd(fsub(f.ahy, phy), fsub(f.aly, ply));
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                qa[l] = ffma(ax, sn[l], -fmul(ay, c[l]));
+                qa[l + 3] = ffma(ax, c[l], fmul(ay, sn[l]));
+                gq[l] = fminf(gq[l], fabsf(qa[l]));
+                gq[l + 3] = fminf(gq[l + 3], fabsf(qa[l + 3]));
+            }
+        }
+        const float bx = fadd(fsub(f.bhx, phx), fsub(f.blx, plx));
+        const float by = fadd(fsub(f.bhy, phy), fsub(f.bly, ply));
+        // cross(e, A - pos) in float64 (two FMAs on the FP64 pipe), then one float32 reciprocal
+        const double un64 = dfma(g.ey, s.px, dfma(-g.ex, s.py, g.K));
+        const float inv = frcp((float)un64);
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const float qb0 = ffma(bx, sn[l], -fmul(by, c[l]));
+            const float qb3 = ffma(bx, c[l], fmul(by, sn[l]));
+            const float r0 = fmul(ffma(f.ex, sn[l], -fmul(f.ey, c[l])), inv);   // cross(e,d)/cross(e,A')
+            const float r3 = fmul(ffma(f.ex, c[l], fmul(f.ey, sn[l])), inv);
+            if (fmul(qa[l], qb0) < 0.0f) { Rp[l] = fmaxf(Rp[l], r0); Rm[l] = fminf(Rm[l], r0); }
+            if (fmul(qa[l + 3], qb3) < 0.0f) { Rp[l + 3] = fmaxf(Rp[l + 3], r3); Rm[l + 3] = fminf(Rm[l + 3], r3); }
+            gq[l] = fminf(gq[l], fabsf(qb0));
+            gq[l + 3] = fminf(gq[l + 3], fabsf(qb3));
+            qa[l] = qb0; qa[l + 3] = qb3;
+        }
+    }
+
+    // ---- decisions ---------------------------------------------------------------------------
+    const float r_tiny = frcp(P.tiny_d);
+    const float r_coll = 0.1f;                    // d < 10  <=>  1/d > 0.1
+    const float r_band = fmul(r_coll, P.coll_band);
+    bool destroyed = false;
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+        const bool cardinal = (l == 0 || l == 3);
+        bool redo = gq[l] < P.eps_q;
+        if (redo) stat_add(stats, kStatLine);
+        if (!redo && (Rp[l] > r_tiny || Rm[l] < -r_tiny)) { redo = true; stat_add(stats, kStatTiny); }
+        if (!redo && cardinal && (fabsf(fsub(Rp[l], r_coll)) < r_band || fabsf(fadd(Rm[l], r_coll)) < r_band)) {
+            redo = true; stat_add(stats, kStatBand);
+        }
+        if (!redo) {
+            dist[l] = Rp[l] > R0 ? frcp(Rp[l]) : 1000.0f;
+            dist[l + 6] = Rm[l] < -R0 ? -frcp(Rm[l]) : 1000.0f;
+            if (cardinal) destroyed = destroyed || (Rp[l] > r_coll) || (Rm[l] < -r_coll);
+        } else {
+            const D2 d0 = T.trig64[wrap72(s.k + 6 * l)], d1 = T.trig64[wrap72(s.k + 6 * l + 36)];
+            const double e0 = exact_ray_distance(s.px, s.py, d0.x, d0.y, T.walls64, P.n_seg);
+            const double e1 = exact_ray_distance(s.px, s.py, d1.x, d1.y, T.walls64, P.n_seg);
+            dist[l] = (float)e0; dist[l + 6] = (float)e1;
+            if (cardinal) destroyed = destroyed || (e0 < 10.0) || (e1 < 10.0);
+        }
+    }
+    return destroyed;
+}
+
+// ---- one CarEnv.step with same-step autoreset --------------------------------------------------
+CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackParams &P, const Tables &T,
+                    StepResult &o, unsigned long long *stats) {
+    int thrust, turn;
+    decode_action(action, thrust, turn);
+    double reward = thrust > 0 ? 0.01 : 0.0;
+    const int k_pre = s.k;
+
+    // gate bookkeeping: uses the pose BEFORE this step's turn and move (rays are only refreshed in update)
+    o.gate_hit = 0; o.lap = 0;
+    if (gate_touched(s, P, T, stats)) {
+        reward = dadd(reward, 1.0);
+        s.passed += 1;
+        o.gate_hit = 1;
+        if (s.next_gate == P.n_gates - 1) { reward = dadd(reward, 10.0); s.next_gate = 0; o.lap = 1; }
+        else s.next_gate += 1;
+    }
+    s.k = wrap72(s.k + turn);
+    integrate(s, thrust, k_pre, T);
+
+    float dist[kNumRays];
+    bool destroyed = cast_walls(s, P, T, dist, stats);
+    destroyed = destroyed || (P.start_destroyed != 0);
+    s.t += 1;
+    o.terminated = 0; o.truncated = 0;
+    if (destroyed) { o.terminated = 1; reward = dsub(reward, 3.0); }
+    else if (s.t >= kTimeLimit) o.truncated = 1;
+    o.reward = (float)dmul(reward, reward_scale);
+    o.gates_passed = s.passed; o.time_passed = s.t; o.next_gate = s.next_gate;
+
+    if (o.terminated | o.truncated) {
+        s.px = P.start_x; s.py = P.start_y; s.vx = 0.0; s.vy = 0.0;
+        s.k = 0; s.t = 0; s.next_gate = 0; s.passed = 0;
+#pragma unroll
+        for (int i = 0; i < kObsDim; ++i) o.obs[i] = P.reset_obs[i];
+    } else {
+        const F2 d = T.trig32[s.k];
+        o.obs[0] = (float)dmul(s.px, 1.0 / 1280.0);
+        o.obs[1] = (float)dmul(s.py, 1.0 / 720.0);
+        o.obs[2] = (float)dmul(s.vx, 0.1);
+        o.obs[3] = (float)dmul(s.vy, 0.1);
+        o.obs[4] = d.x; o.obs[5] = d.y;
+#pragma unroll
+        for (int i = 0; i < kNumRays; ++i) o.obs[6 + i] = fmul(dist[i], 1.0e-3f);
+    }
+}
+
+// Observation of the start pose (what CarEnv.reset returns, lib/car_env.py:682-688), evaluated
+// with the literal float64 formulas; also tells whether the start pose already collides.
+CE_HD bool reset_observation(const TrackParams &P, const Tables &T, float obs[kObsDim]) {
+    obs[0] = (float)(P.start_x / 1280.0); obs[1] = (float)(P.start_y / 720.0);
+    obs[2] = 0.0f; obs[3] = 0.0f;
+    obs[4] = (float)T.trig64[0].x; obs[5] = (float)T.trig64[0].y;
+    bool destroyed = false;
+    for (int i = 0; i < kNumRays; ++i) {
+        const D2 d = T.trig64[wrap72(6 * i)];
+        const double e = exact_ray_distance(P.start_x, P.start_y, d.x, d.y, T.walls64, P.n_seg);
+        obs[6 + i] = (float)(e / 1000.0);
+        if (i % 3 == 0 && e < 10.0) destroyed = true;
+    }
+    return destroyed;
+}
+
+}  // namespace carenv

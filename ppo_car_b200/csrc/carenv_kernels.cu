@@ -1,0 +1,393 @@
+// carenv_kernels.cu — sm_100a kernels and the C ABI of libcarenv_b200.so (include/carenv_b200.h).
+//
+//   k_rollout   one thread per environment, n_steps >= 1 CarEnv.step calls per launch with the
+//               state held in registers between steps (carenv_step is the n_steps == 1 case).
+//               Wall geometry lives in kernel-parameter (constant-bank) space so that every
+//               segment coordinate is a uniform operand of the FMA-pipe instructions; the
+//               per-thread-indexed tables (72 headings, gates) are staged once per block into
+//               shared memory.
+//   k_reset     CarEnv.reset for every environment.
+//   k_gae       Buffer.calculate_advantages as a reverse scan, one thread per environment column.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/carenv_b200.h"
+#include "carenv_tables.h"
+
+using namespace carenv;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return -1000 - (int)e;
+}
+#define CU(call)                                          \
+    do {                                                  \
+        cudaError_t _e = (call);                          \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+    } while (0)
+
+struct Handle {
+    int device;
+    HostTrack host;
+    unsigned char *d_blob;    // trig64 | acc64 | gates | trig32 | walls64
+    Tables dev;               // device pointers into d_blob
+    unsigned long long *d_stats;
+    size_t smem_bytes;
+};
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+constexpr int kBlock = 128;
+
+template <typename FlagT> __device__ __forceinline__ FlagT make_flag(int v);
+template <> __device__ __forceinline__ uint8_t make_flag<uint8_t>(int v) { return (uint8_t)v; }
+template <> __device__ __forceinline__ float make_flag<float>(int v) { return v ? 1.0f : 0.0f; }
+
+// Stage the per-thread-indexed tables into shared memory (all sizes are multiples of 8 bytes).
+__device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, unsigned char *smem) {
+    D2 *s_trig64 = reinterpret_cast<D2 *>(smem);
+    D2 *s_acc64 = s_trig64 + kHeadings;
+    GateRec *s_gates = reinterpret_cast<GateRec *>(s_acc64 + kHeadings);
+    F2 *s_trig32 = reinterpret_cast<F2 *>(s_gates + n_gates);
+    const int n64a = kHeadings * 2, n64g = n_gates * (int)(sizeof(GateRec) / 8);
+    double *d0 = reinterpret_cast<double *>(s_trig64);
+    double *d1 = reinterpret_cast<double *>(s_acc64);
+    double *d2 = reinterpret_cast<double *>(s_gates);
+    double *d3 = reinterpret_cast<double *>(s_trig32);
+    const double *g0 = reinterpret_cast<const double *>(G.trig64);
+    const double *g1 = reinterpret_cast<const double *>(G.acc64);
+    const double *g2 = reinterpret_cast<const double *>(G.gates);
+    const double *g3 = reinterpret_cast<const double *>(G.trig32);
+    for (int i = threadIdx.x; i < n64a; i += blockDim.x) { d0[i] = g0[i]; d1[i] = g1[i]; }
+    for (int i = threadIdx.x; i < n64g; i += blockDim.x) d2[i] = g2[i];
+    for (int i = threadIdx.x; i < kHeadings; i += blockDim.x) d3[i] = g3[i];
+    __syncthreads();
+    return Tables{s_trig32, s_trig64, s_acc64, s_gates, G.walls64};
+}
+
+template <typename ActT, typename FlagT>
+__global__ void __launch_bounds__(kBlock)
+k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int n_steps, double2 *__restrict__ pos,
+          double2 *__restrict__ vel, int4 *__restrict__ ints, const ActT *__restrict__ actions, double reward_scale,
+          float *__restrict__ obs_out, float *__restrict__ rew_out, FlagT *__restrict__ term_out,
+          FlagT *__restrict__ trunc_out, int4 *__restrict__ info_out, unsigned long long *stats) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables T = stage_tables(G, P.n_gates, smem);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+
+    EnvState s;
+    {
+        const double2 p = pos[e], v = vel[e];
+        const int4 q = ints[e];
+        s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
+        s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
+    }
+    for (int t = 0; t < n_steps; ++t) {
+        const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+        const int a = (int)actions[idx];
+        StepResult o;
+        env_step(s, a, reward_scale, P, T, o, stats);
+        if (obs_out) {
+            float2 *dst = reinterpret_cast<float2 *>(obs_out + idx * kObsDim);
+#pragma unroll
+            for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(o.obs[2 * i], o.obs[2 * i + 1]);
+        }
+        rew_out[idx] = o.reward;
+        term_out[idx] = make_flag<FlagT>(o.terminated);
+        trunc_out[idx] = make_flag<FlagT>(o.truncated);
+        if (info_out) info_out[idx] = make_int4(o.gates_passed, o.time_passed, o.next_gate, o.gate_hit | (o.lap << 1));
+    }
+    pos[e] = make_double2(s.px, s.py);
+    vel[e] = make_double2(s.vx, s.vy);
+    ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_reset(const __grid_constant__ TrackParams P, int n_envs, double2 *__restrict__ pos, double2 *__restrict__ vel,
+        int4 *__restrict__ ints, float *__restrict__ obs_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+    pos[e] = make_double2(P.start_x, P.start_y);
+    vel[e] = make_double2(0.0, 0.0);
+    ints[e] = make_int4(0, 0, 0, 0);
+    if (obs_out) {
+        float2 *dst = reinterpret_cast<float2 *>(obs_out + (size_t)e * kObsDim);
+#pragma unroll
+        for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(P.reset_obs[2 * i], P.reset_obs[2 * i + 1]);
+    }
+}
+
+// GAE(lambda), lib/buffer.py:51-63.  The recurrence is serial in t but the loads are not: the
+// loop is unrolled so that kGaeUnroll timesteps of loads are in flight per thread.
+constexpr int kGaeUnroll = 8;
+__global__ void __launch_bounds__(256)
+k_gae(const float *__restrict__ rew, const float *__restrict__ val, const float *__restrict__ term,
+      const float *__restrict__ trunc, const float *__restrict__ last_val, const float *__restrict__ last_term,
+      const float *__restrict__ last_trunc, float *__restrict__ adv, float *__restrict__ ret, int T, int N, float g,
+      float gl) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    float nv = last_val[e];
+    float tm = __fadd_rn(1.0f, -last_term[e]);
+    float um = __fadd_rn(1.0f, -last_trunc[e]);
+    float a = 0.0f;
+    int t = T - 1;
+    for (; t >= kGaeUnroll - 1; t -= kGaeUnroll) {
+        float r[kGaeUnroll], v[kGaeUnroll], te[kGaeUnroll], tr[kGaeUnroll];
+#pragma unroll
+        for (int i = 0; i < kGaeUnroll; ++i) {
+            const size_t k = (size_t)(t - i) * (size_t)N + (size_t)e;
+            r[i] = __ldcs(rew + k); v[i] = __ldcs(val + k); te[i] = __ldcs(term + k); tr[i] = __ldcs(trunc + k);
+        }
+#pragma unroll
+        for (int i = 0; i < kGaeUnroll; ++i) {
+            const size_t k = (size_t)(t - i) * (size_t)N + (size_t)e;
+            const float delta = __fadd_rn(__fadd_rn(r[i], __fmul_rn(__fmul_rn(g, nv), tm)), -v[i]);
+            a = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(gl, tm), um), a));
+            __stcs(adv + k, a);
+            __stcs(ret + k, __fadd_rn(a, v[i]));
+            nv = v[i];
+            tm = __fadd_rn(1.0f, -te[i]);
+            um = __fadd_rn(1.0f, -tr[i]);
+        }
+    }
+    for (; t >= 0; --t) {
+        const size_t k = (size_t)t * (size_t)N + (size_t)e;
+        const float r = __ldcs(rew + k), v = __ldcs(val + k);
+        const float delta = __fadd_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g, nv), tm)), -v);
+        a = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(gl, tm), um), a));
+        __stcs(adv + k, a);
+        __stcs(ret + k, __fadd_rn(a, v));
+        nv = v;
+        tm = __fadd_rn(1.0f, -__ldcs(term + k));
+        um = __fadd_rn(1.0f, -__ldcs(trunc + k));
+    }
+}
+
+// FP32-pipe peak probe: kFfmaChains independent FFMA chains per thread, no memory traffic.
+// MEASURED_PEAKS.json has no FP32 entry, so bench.py measures one beside the nominal.
+constexpr int kFfmaChains = 8;
+__global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float a, float b) {
+    float acc[kFfmaChains];
+#pragma unroll
+    for (int i = 0; i < kFfmaChains; ++i) acc[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < kFfmaChains; ++i) acc[i] = __fmaf_rn(acc[i], a, b);
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kFfmaChains; ++i) sum += acc[i];
+    if (sum == 12345.678f) out[0] = sum;   // keeps the chains alive without storing
+}
+
+template <typename ActT, typename FlagT>
+int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints, const void *actions,
+                   double reward_scale, float *obs_out, float *reward_out, void *term_out, void *trunc_out,
+                   int32_t *info_out, cudaStream_t stream) {
+    auto kern = k_rollout<ActT, FlagT>;
+    if (h->smem_bytes > 48 * 1024)
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    const int grid = (n_envs + kBlock - 1) / kBlock;
+    kern<<<grid, kBlock, h->smem_bytes, stream>>>(
+        h->host.P, h->dev, n_envs, n_steps, reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel),
+        reinterpret_cast<int4 *>(ints), static_cast<const ActT *>(actions), reward_scale, obs_out, reward_out,
+        static_cast<FlagT *>(term_out), static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out),
+        h->d_stats);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int dispatch_rollout(void *handle, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints,
+                     const void *actions, int action_dtype, double reward_scale, float *obs_out, float *reward_out,
+                     void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(CARENV_E_INVAL, "null handle");
+    if (n_envs < 0 || n_steps < 0) return fail(CARENV_E_INVAL, "negative n_envs / n_steps");
+    if (n_envs == 0 || n_steps == 0) return 0;
+    if (!pos || !vel || !ints || !actions || !reward_out || !term_out || !trunc_out)
+        return fail(CARENV_E_INVAL, "null state / action / output pointer");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CASE(A, AT, F, FT)                                                                                       \
+    if (action_dtype == A && flag_dtype == F)                                                                    \
+        return launch_rollout<AT, FT>(h, n_envs, n_steps, pos, vel, ints, actions, reward_scale, obs_out,       \
+                                      reward_out, term_out, trunc_out, info_out, st);
+    CASE(CARENV_ACT_U8, uint8_t, CARENV_FLAG_U8, uint8_t)
+    CASE(CARENV_ACT_U8, uint8_t, CARENV_FLAG_F32, float)
+    CASE(CARENV_ACT_I32, int32_t, CARENV_FLAG_U8, uint8_t)
+    CASE(CARENV_ACT_I32, int32_t, CARENV_FLAG_F32, float)
+    CASE(CARENV_ACT_I64, int64_t, CARENV_FLAG_U8, uint8_t)
+    CASE(CARENV_ACT_I64, int64_t, CARENV_FLAG_F32, float)
+#undef CASE
+    return fail(CARENV_E_INVAL, "unknown action_dtype / flag_dtype");
+}
+
+}  // namespace
+
+extern "C" {
+
+int carenv_abi_version(void) { return CARENV_ABI_VERSION; }
+const char *carenv_last_error(void) { return g_err.c_str(); }
+
+int carenv_create(const double *walls, int n_walls, const double *gates, int n_gates, double init_x, double init_y,
+                  double init_angle_deg, int device, void **handle) {
+    if (!handle) return fail(CARENV_E_INVAL, "null handle pointer");
+    *handle = nullptr;
+    if (!walls || !gates) return fail(CARENV_E_INVAL, "null geometry pointer");
+    if (n_walls < 1 || n_walls > CARENV_MAX_SEGMENTS)
+        return fail(CARENV_E_TRACK, "number of wall segments must be in 1.." + std::to_string(CARENV_MAX_SEGMENTS));
+    if (n_gates < 1 || n_gates > 4000) return fail(CARENV_E_TRACK, "number of gates must be in 1..4000");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1) return fail(CARENV_E_NOGPU, "no CUDA device");
+    if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
+    Handle *h = new Handle();
+    h->device = device;
+    h->d_blob = nullptr; h->d_stats = nullptr;
+    if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
+        delete h;
+        return fail(CARENV_E_TRACK, "malformed track");
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) { delete h; return fail(CARENV_E_NOGPU, "cannot select CUDA device"); }
+    const size_t b_trig64 = sizeof(D2) * kHeadings, b_acc = sizeof(D2) * kHeadings;
+    const size_t b_gates = sizeof(GateRec) * (size_t)n_gates, b_trig32 = sizeof(F2) * kHeadings;
+    const size_t b_walls = sizeof(double) * 4 * (size_t)n_walls;
+    const size_t o_acc = b_trig64, o_gates = o_acc + b_acc, o_trig32 = o_gates + b_gates, o_walls = o_trig32 + b_trig32;
+    h->smem_bytes = o_walls;   // everything except the float64 walls is staged to shared memory
+    cudaError_t e = cudaMalloc(&h->d_blob, o_walls + b_walls);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_stats, sizeof(unsigned long long) * kNumStats);
+    if (e == cudaSuccess) e = cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * kNumStats);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_blob, h->host.trig64.data(), b_trig64, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_acc, h->host.acc64.data(), b_acc, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_gates, h->host.gates.data(), b_gates, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_trig32, h->host.trig32.data(), b_trig32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_walls, h->host.walls64.data(), b_walls, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(h->d_blob); cudaFree(h->d_stats);
+        delete h;
+        return cuda_fail(e, "carenv_create: device allocation / upload");
+    }
+    h->dev.trig64 = reinterpret_cast<const D2 *>(h->d_blob);
+    h->dev.acc64 = reinterpret_cast<const D2 *>(h->d_blob + o_acc);
+    h->dev.gates = reinterpret_cast<const GateRec *>(h->d_blob + o_gates);
+    h->dev.trig32 = reinterpret_cast<const F2 *>(h->d_blob + o_trig32);
+    h->dev.walls64 = reinterpret_cast<const double *>(h->d_blob + o_walls);
+    *handle = h;
+    return 0;
+}
+
+int carenv_destroy(void *handle) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return 0;
+    {
+        DeviceGuard guard(h->device);
+        cudaFree(h->d_blob);
+        cudaFree(h->d_stats);
+    }
+    delete h;
+    return 0;
+}
+
+int carenv_reset_obs(void *handle, float *obs18_host) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !obs18_host) return fail(CARENV_E_INVAL, "null argument");
+    for (int i = 0; i < kObsDim; ++i) obs18_host[i] = h->host.P.reset_obs[i];
+    return 0;
+}
+
+int carenv_reset(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, float *obs_out, void *stream) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(CARENV_E_INVAL, "null handle");
+    if (n_envs < 0) return fail(CARENV_E_INVAL, "negative n_envs");
+    if (n_envs == 0) return 0;
+    if (!pos || !vel || !ints) return fail(CARENV_E_INVAL, "null state pointer");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    const int grid = (n_envs + kBlock - 1) / kBlock;
+    k_reset<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->host.P, n_envs, reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel),
+        reinterpret_cast<int4 *>(ints), obs_out);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int carenv_step(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions,
+                int action_dtype, double reward_scale, float *obs_out, float *reward_out, void *term_out,
+                void *trunc_out, int flag_dtype, int32_t *info_out, void *stream) {
+    if (!obs_out) return fail(CARENV_E_INVAL, "carenv_step needs obs_out");
+    return dispatch_rollout(handle, n_envs, 1, pos, vel, ints, actions, action_dtype, reward_scale, obs_out,
+                            reward_out, term_out, trunc_out, flag_dtype, info_out, stream);
+}
+
+int carenv_rollout(void *handle, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints,
+                   const void *actions, int action_dtype, double reward_scale, float *obs_out, float *reward_out,
+                   void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream) {
+    return dispatch_rollout(handle, n_envs, n_steps, pos, vel, ints, actions, action_dtype, reward_scale, obs_out,
+                            reward_out, term_out, trunc_out, flag_dtype, info_out, stream);
+}
+
+int carenv_stats(void *handle, unsigned long long out[4], int reset_counters) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !out) return fail(CARENV_E_INVAL, "null argument");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, h->d_stats, sizeof(unsigned long long) * kNumStats, cudaMemcpyDeviceToHost));
+    if (reset_counters) CU(cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * kNumStats));
+    return 0;
+}
+
+int gae_reverse_scan(const float *rew, const float *val, const float *term, const float *trunc,
+                     const float *last_val, const float *last_term, const float *last_trunc, float *adv, float *ret,
+                     int T, int N, double gamma, double gae_lambda, void *stream) {
+    if (T < 0 || N < 0) return fail(CARENV_E_INVAL, "negative T / N");
+    if (T == 0 || N == 0) return 0;
+    if (!rew || !val || !term || !trunc || !last_val || !last_term || !last_trunc || !adv || !ret)
+        return fail(CARENV_E_INVAL, "null pointer");
+    const float g = (float)gamma;
+    const float gl = (float)(gamma * gae_lambda);   // evaluated in double first (lib/buffer.py:61)
+    const int grid = (N + 255) / 256;
+    k_gae<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(rew, val, term, trunc, last_val, last_term, last_trunc,
+                                                              adv, ret, T, N, g, gl);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+/* Measurement helper: launches blocks x 256 threads, each doing iters * 64 FFMA (2 flop each). */
+int carenv_bench_ffma(int blocks, int iters, float *scratch, void *stream) {
+    if (blocks < 1 || iters < 1 || !scratch) return fail(CARENV_E_INVAL, "bad argument");
+    k_ffma_peak<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(scratch, iters, 0.999f, 0.001f);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// carenv_tables.h — host-side preparation of the per-track constants (runs once per handle).
+//
+// Input is the track exactly as the reference builds it in CarEnv.reset
+// (lib/car_env.py:651-676): wall segments in pixel coordinates, outer polyline first then
+// inner, gates from consecutive point pairs, the start pose in pixels / degrees.
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "carenv_core.cuh"
+
+namespace carenv {
+
+struct HostTrack {
+    TrackParams P;
+    std::vector<F2> trig32;
+    std::vector<D2> trig64, acc64;
+    std::vector<GateRec> gates;
+    std::vector<double> walls64;
+    Tables tables() const { return Tables{trig32.data(), trig64.data(), acc64.data(), gates.data(), walls64.data()}; }
+};
+
+inline void split_hi_lo(double v, float &hi, float &lo) {
+    hi = (float)v;
+    lo = (float)(v - (double)hi);
+}
+
+// returns 0 on success, <0 on invalid input
+inline int build_host_track(const double *walls, int n_walls, const double *gates, int n_gates,
+                            double sx, double sy, double angle_deg, HostTrack &H) {
+    if (n_walls < 1 || n_walls > kMaxSeg || n_gates < 1 || !walls || !gates) return -1;
+    memset(&H.P, 0, sizeof(H.P));
+    TrackParams &P = H.P;
+    P.n_seg = n_walls; P.n_gates = n_gates;
+    P.start_x = sx; P.start_y = sy;
+
+    const double DEG = M_PI / 180.0;   // np.radians
+    H.trig32.resize(kHeadings); H.trig64.resize(kHeadings); H.acc64.resize(kHeadings);
+    for (int k = 0; k < kHeadings; ++k) {
+        const double ang = angle_deg + 5.0 * k;
+        const double c = cos(ang * DEG), s = sin(ang * DEG);
+        H.trig64[k] = D2{c, s};
+        H.trig32[k] = F2{(float)c, (float)s};
+        H.acc64[k] = D2{c * 0.8, s * 0.8};
+    }
+
+    H.walls64.assign(walls, walls + 4 * (size_t)n_walls);
+    double min_sin = 1.0;
+    for (int j = 0; j < n_walls; ++j) {
+        const double ax = walls[4 * j], ay = walls[4 * j + 1], bx = walls[4 * j + 2], by = walls[4 * j + 3];
+        SegF &f = P.segf[j];
+        split_hi_lo(ax, f.ahx, f.alx); split_hi_lo(ay, f.ahy, f.aly);
+        split_hi_lo(bx, f.bhx, f.blx); split_hi_lo(by, f.bhy, f.bly);
+        const double ex = bx - ax, ey = by - ay;
+        f.ex = (float)ex; f.ey = (float)ey;
+        f.chain_start = (j == 0 || walls[4 * j - 2] != ax || walls[4 * j - 1] != ay) ? 1 : 0;
+        P.segd[j] = SegD{fma(ex, ay, -(ey * ax)), ex, ey};
+        const double len = hypot(ex, ey);
+        if (len > 0)
+            for (int k = 0; k < kHeadings; ++k) {
+                const double sn = fabs(ex * H.trig64[k].y - ey * H.trig64[k].x) / len;
+                if (sn > 1e-7 && sn < min_sin) min_sin = sn;   // exactly parallel pairs cannot be hit
+            }
+    }
+
+    H.gates.resize(n_gates);
+    for (int g = 0; g < n_gates; ++g) {
+        GateRec &r = H.gates[g];
+        r.x1 = gates[4 * g]; r.y1 = gates[4 * g + 1]; r.x2 = gates[4 * g + 2]; r.y2 = gates[4 * g + 3];
+        const double ex = r.x2 - r.x1, ey = r.y2 - r.y1;
+        r.ex = (float)ex; r.ey = (float)ey; r.len = (float)hypot(ex, ey); r.pad = 0.0f;
+    }
+
+    // guard bands: bounds on the float32 error of q, r and the gate margin
+    P.eps_q = 1.0e-3f;      // |dq| <= 5.3 * 2^-24 * |P - pos| <= 4.7e-4 px for |P - pos| <= 1500 px
+    const double rel_r = 2.5e-7 / min_sin + 3.0e-7;   // relative error of r = cross(e,d) / cross(e,A')
+    P.coll_band = (float)fmax(1.0e-3, 4.0 * rel_r);
+    P.tiny_d = 1.0e-2f;
+    P.gate_band = 2.0e-3f;
+
+    const Tables T = H.tables();
+    P.start_destroyed = reset_observation(P, T, P.reset_obs) ? 1 : 0;
+    return 0;
+}
+
+}  // namespace carenv

@@ -1,0 +1,254 @@
+"""VecCarEnv — the batched, auto-resetting CarEnv on one B200.
+
+Drop-in for what train.py does with ``gym.vector.AsyncVectorEnv([make_env]*n_envs)``
+(/root/reference/train.py:138-142, 159, 185, 296): ``single_observation_space``,
+``single_action_space``, ``reset(options={"track_path": ...})``, ``step(actions)`` returning
+the 5-tuple with same-step autoreset, ``close()``.  ``reward_scaling`` stands in for the
+``TransformReward`` wrapper (train.py:65, 68).
+
+All state and outputs are PyTorch CUDA tensors; the arithmetic runs in the hand-written
+sm_100a kernels of libcarenv_b200.so.  There is no CPU path: constructing a VecCarEnv
+without the built library or without a CUDA device raises.
+
+Two calling conventions for ``step``:
+  * CUDA tensor in  -> CUDA tensors out (no host round trip; int64/int32/uint8 actions).
+  * numpy array in  -> numpy arrays out (the reference's convention, train.py:185): actions are
+    staged through pinned host memory, results are copied back into pinned buffers and
+    returned as numpy views that stay valid until the next call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .track import Track, builtin_track, load_track
+
+OBS_DIM = 18
+N_ACTIONS = 9
+
+
+class Box:
+    """Minimal stand-in for gymnasium.spaces.Box (lib/car_env.py:513-524)."""
+
+    def __init__(self, low, high, dtype=np.float32):
+        self.low, self.high, self.dtype = np.asarray(low, dtype), np.asarray(high, dtype), dtype
+        self.shape = self.low.shape
+
+
+class Discrete:
+    """Minimal stand-in for gymnasium.spaces.Discrete (lib/car_env.py:525)."""
+
+    def __init__(self, n: int):
+        self.n = n
+        self.shape = ()
+
+
+_ACT_CODES = {torch.uint8: _lib.ACT_U8, torch.int32: _lib.ACT_I32, torch.int64: _lib.ACT_I64}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class VecCarEnv:
+    def __init__(self, n_envs: int, track_path: str | None = None, device="cuda", reward_scaling: float = 1.0,
+                 float_flags: bool = False, with_info: bool = True):
+        if n_envs < 1:
+            raise ValueError("n_envs must be >= 1")
+        self._L = _lib.lib()                       # raises if the CUDA extension is missing
+        if not torch.cuda.is_available():
+            raise _lib.CarEnvError("VecCarEnv needs a CUDA device (there is no CPU implementation)")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.CarEnvError("VecCarEnv only runs on CUDA devices")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = int(n_envs)
+        self.reward_scaling = float(reward_scaling)
+        self.float_flags = bool(float_flags)
+        self.with_info = bool(with_info)
+        low = np.array([0, 0, -1, -1, -1, -1] + [0] * 12, np.float32)
+        high = np.ones(OBS_DIM, np.float32)
+        self.single_observation_space = Box(low, high)
+        self.single_action_space = Discrete(N_ACTIONS)
+        self.observation_space, self.action_space = self.single_observation_space, self.single_action_space
+        self._handle = None
+        self.track: Track | None = None
+        n, dev = self.num_envs, self.device
+        # structure-of-arrays state, owned by PyTorch (include/carenv_b200.h)
+        self.pos = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+        self.vel = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+        self.ints = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+        fdt = torch.float32 if self.float_flags else torch.uint8
+        self._obs = torch.empty((n, OBS_DIM), dtype=torch.float32, device=dev)
+        self._rew = torch.empty((n,), dtype=torch.float32, device=dev)
+        self._term = torch.empty((n,), dtype=fdt, device=dev)
+        self._trunc = torch.empty((n,), dtype=fdt, device=dev)
+        self._info = torch.empty((n, 4), dtype=torch.int32, device=dev) if self.with_info else None
+        self._host = None                          # pinned staging buffers, created on first numpy call
+        self._needs_reset = True
+        self._set_track(track_path or builtin_track("track"))   # reference default: tracks/track.json
+
+    # ------------------------------------------------------------------ track / handle
+    def _set_track(self, path: str) -> None:
+        track = load_track(path)
+        handle = C.c_void_p()
+        walls = np.ascontiguousarray(track.walls, np.float64)
+        gates = np.ascontiguousarray(track.gates, np.float64)
+        rc = self._L.carenv_create(walls.ctypes.data_as(C.c_void_p), len(walls), gates.ctypes.data_as(C.c_void_p),
+                                   len(gates), track.start[0], track.start[1], track.angle, self.device.index,
+                                   C.byref(handle))
+        _lib.check(rc, "carenv_create")
+        if self._handle is not None:
+            self._L.carenv_destroy(self._handle)
+        self._handle, self.track = handle, track
+        self._needs_reset = True
+
+    @property
+    def reset_observation(self) -> np.ndarray:
+        out = np.zeros(OBS_DIM, np.float32)
+        _lib.check(self._L.carenv_reset_obs(self._handle, out.ctypes.data_as(C.c_void_p)), "carenv_reset_obs")
+        return out
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ gym-style API
+    def reset(self, seed=None, options=None):
+        """CarEnv.reset for every environment (lib/car_env.py:605-691).  ``seed`` is accepted and
+        ignored exactly like in the reference: the environment has no randomness."""
+        if options and "track_path" in options:
+            self._set_track(options["track_path"])
+        with torch.cuda.device(self.device):
+            rc = self._L.carenv_reset(self._handle, self.num_envs, _ptr(self.pos), _ptr(self.vel), _ptr(self.ints),
+                                      _ptr(self._obs), self._stream())
+        _lib.check(rc, "carenv_reset")
+        self._needs_reset = False
+        zeros = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        return self._obs, {"gates_passed": zeros, "time_passed": zeros.clone()}
+
+    def _info_dict(self, info):
+        if info is None:
+            return {}
+        return {"gates_passed": info[..., 0], "time_passed": info[..., 1], "next_gate_index": info[..., 2],
+                "gate_hit": info[..., 3] & 1, "lap": (info[..., 3] >> 1) & 1}
+
+    def step(self, actions):
+        """One step of every environment with same-step autoreset (lib/car_env.py:693-760 +
+        gymnasium AsyncVectorEnv).  Returns (obs, rewards, terminateds, truncateds, info)."""
+        if self._needs_reset:
+            raise _lib.CarEnvError("call reset() before step()")
+        if isinstance(actions, torch.Tensor) and actions.is_cuda:
+            return self._step_device(actions)
+        return self._step_host(np.asarray(actions))
+
+    def _step_device(self, actions: torch.Tensor):
+        if actions.dtype not in _ACT_CODES:
+            actions = actions.to(torch.int64)
+        actions = actions.reshape(-1)
+        if actions.numel() != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} actions, got {actions.numel()}")
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
+        with torch.cuda.device(self.device):
+            rc = self._L.carenv_step(self._handle, self.num_envs, _ptr(self.pos), _ptr(self.vel), _ptr(self.ints),
+                                     _ptr(actions), _ACT_CODES[actions.dtype], self.reward_scaling, _ptr(self._obs),
+                                     _ptr(self._rew), _ptr(self._term), _ptr(self._trunc),
+                                     _lib.FLAG_F32 if self.float_flags else _lib.FLAG_U8, _ptr(self._info),
+                                     self._stream())
+        _lib.check(rc, "carenv_step")
+        term = self._term if self.float_flags else self._term.view(torch.bool)
+        trunc = self._trunc if self.float_flags else self._trunc.view(torch.bool)
+        return self._obs, self._rew, term, trunc, self._info_dict(self._info)
+
+    def _step_host(self, actions: np.ndarray):
+        n = self.num_envs
+        if actions.size != n:
+            raise ValueError(f"expected {n} actions, got {actions.size}")
+        if self._host is None:
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+            self._host = dict(act=pin((n,), torch.uint8), obs=pin((n, OBS_DIM), torch.float32),
+                              rew=pin((n,), torch.float32), term=pin((n,), self._term.dtype),
+                              trunc=pin((n,), self._trunc.dtype),
+                              info=pin((n, 4), torch.int32) if self.with_info else None,
+                              dact=torch.empty((n,), dtype=torch.uint8, device=self.device))
+        h = self._host
+        np.copyto(h["act"].numpy(), actions.reshape(-1), casting="unsafe")
+        h["dact"].copy_(h["act"], non_blocking=True)
+        obs, rew, term, trunc, _ = self._step_device(h["dact"])
+        h["obs"].copy_(obs, non_blocking=True)
+        h["rew"].copy_(rew, non_blocking=True)
+        h["term"].copy_(self._term, non_blocking=True)
+        h["trunc"].copy_(self._trunc, non_blocking=True)
+        if self.with_info:
+            h["info"].copy_(self._info, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        flags = (lambda t: t.numpy()) if self.float_flags else (lambda t: t.numpy().view(np.bool_))
+        info = self._info_dict(h["info"].numpy()) if self.with_info else {}
+        return h["obs"].numpy(), h["rew"].numpy(), flags(h["term"]), flags(h["trunc"]), info
+
+    # ------------------------------------------------------------------ multi-step launch
+    def rollout(self, actions: torch.Tensor, obs_out=None, reward_out=None, term_out=None, trunc_out=None,
+                info_out=None, store_obs: bool = True, store_info: bool = False):
+        """n_steps consecutive steps in one kernel launch (the rollout loop of train.py:173-195 with
+        the actions given up front).  ``actions`` is a CUDA tensor [n_steps, n_envs]; outputs are
+        [n_steps, n_envs(, 18)] CUDA tensors (allocated here unless passed in)."""
+        if self._needs_reset:
+            raise _lib.CarEnvError("call reset() before rollout()")
+        if not (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dim() == 2):
+            raise ValueError("rollout expects a CUDA tensor of shape [n_steps, n_envs]")
+        if actions.dtype not in _ACT_CODES:
+            actions = actions.to(torch.int64)
+        actions = actions.contiguous()
+        K, n = actions.shape
+        if n != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} environments, got {n}")
+        dev = self.device
+        fdt = torch.float32 if self.float_flags else torch.uint8
+        if obs_out is None and store_obs:
+            obs_out = torch.empty((K, n, OBS_DIM), dtype=torch.float32, device=dev)
+        if reward_out is None:
+            reward_out = torch.empty((K, n), dtype=torch.float32, device=dev)
+        if term_out is None:
+            term_out = torch.empty((K, n), dtype=fdt, device=dev)
+        if trunc_out is None:
+            trunc_out = torch.empty((K, n), dtype=fdt, device=dev)
+        if info_out is None and store_info:
+            info_out = torch.empty((K, n, 4), dtype=torch.int32, device=dev)
+        for name, t, shape, dt in (("obs_out", obs_out, (K, n, OBS_DIM), torch.float32),
+                                   ("reward_out", reward_out, (K, n), torch.float32),
+                                   ("term_out", term_out, (K, n), fdt), ("trunc_out", trunc_out, (K, n), fdt),
+                                   ("info_out", info_out, (K, n, 4), torch.int32)):
+            if t is not None and (tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or not t.is_cuda):
+                raise ValueError(f"{name} must be a contiguous CUDA tensor of shape {shape} and dtype {dt}")
+        with torch.cuda.device(dev):
+            rc = self._L.carenv_rollout(self._handle, n, K, _ptr(self.pos), _ptr(self.vel), _ptr(self.ints),
+                                        _ptr(actions), _ACT_CODES[actions.dtype], self.reward_scaling, _ptr(obs_out),
+                                        _ptr(reward_out), _ptr(term_out), _ptr(trunc_out),
+                                        _lib.FLAG_F32 if self.float_flags else _lib.FLAG_U8, _ptr(info_out),
+                                        self._stream())
+        _lib.check(rc, "carenv_rollout")
+        out = {"obs": obs_out, "reward": reward_out, "terminated": term_out, "truncated": trunc_out}
+        if info_out is not None:
+            out["info"] = self._info_dict(info_out)
+        return out
+
+    def slow_path_counts(self, reset: bool = True) -> dict:
+        """How often the float64 re-evaluation ran since the last call (synchronises)."""
+        out = (C.c_ulonglong * 4)()
+        _lib.check(self._L.carenv_stats(self._handle, out, int(reset)), "carenv_stats")
+        return {"line": out[0], "band": out[1], "gate": out[2], "tiny": out[3]}
+
+    def close(self):
+        if self._handle is not None:
+            self._L.carenv_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

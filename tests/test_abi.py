@@ -1,0 +1,79 @@
+"""CPU-only: the C-ABI library builds for sm_100a, loads, exports every symbol the header declares,
+and fails loudly (no CPU fallback) when there is no GPU.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import ppo_car_b200
+from ppo_car_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "carenv_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:int|const char \*)\s*\*?\s*(carenv_\w+|gae_\w+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = ppo_car_b200.build()
+    assert os.path.exists(path)
+    L = C.CDLL(path)
+    names = declared_functions()
+    assert {"carenv_create", "carenv_destroy", "carenv_reset", "carenv_step", "carenv_rollout", "carenv_reset_obs",
+            "carenv_stats", "gae_reverse_scan", "carenv_last_error", "carenv_abi_version"} <= set(names)
+    for n in names:
+        assert hasattr(L, n), n
+    assert _lib.lib().carenv_abi_version() == 1
+
+
+def test_library_contains_sm100a_code():
+    out = os.popen(f"cuobjdump -lelf {ppo_car_b200.build()} 2>/dev/null").read()
+    assert "sm_100a" in out
+
+
+def test_bad_arguments_return_error_codes():
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.carenv_create(None, 4, None, 1, 0.0, 0.0, 0.0, 0, C.byref(h)) == -1          # CARENV_E_INVAL
+    walls = np.zeros((200, 4))
+    gates = np.zeros((1, 4))
+    rc = L.carenv_create(walls.ctypes.data_as(C.c_void_p), 200, gates.ctypes.data_as(C.c_void_p), 1, 0.0, 0.0, 0.0,
+                         0, C.byref(h))
+    assert rc == -2 and b"segments" in L.carenv_last_error()                               # CARENV_E_TRACK
+    assert L.carenv_step(None, 1, None, None, None, None, 0, 1.0, None, None, None, None, 0, None, None) < 0
+    assert L.gae_reverse_scan(*([None] * 9), 4, 4, 0.99, 0.95, None) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(ppo_car_b200.CarEnvError):
+        ppo_car_b200.VecCarEnv(4, ppo_car_b200.builtin_track("track"))
+    with pytest.raises(ppo_car_b200.CarEnvError):
+        ppo_car_b200.Buffer((18,), 8, 4, "cpu")
+    with pytest.raises(ppo_car_b200.CarEnvError):
+        z = torch.zeros(4, 4)
+        ppo_car_b200.gae_reverse_scan(z, z, z, z, z[0], z[0], z[0])
+    L = _lib.lib()
+    tr = ppo_car_b200.load_track(ppo_car_b200.builtin_track("track"))
+    h = C.c_void_p()
+    rc = L.carenv_create(tr.walls.ctypes.data_as(C.c_void_p), len(tr.walls), tr.gates.ctypes.data_as(C.c_void_p),
+                         len(tr.gates), tr.start[0], tr.start[1], tr.angle, 0, C.byref(h))
+    assert rc == -3 and not h.value                                                        # CARENV_E_NOGPU
+
+
+def test_track_loader_matches_reference_construction(tracks_dir):
+    from oracle.carenv_port import load_track as port_load
+
+    for name in ("track", "big_track"):
+        p = os.path.join(tracks_dir, name + ".json")
+        a, b = ppo_car_b200.load_track(p), port_load(p)
+        assert np.array_equal(a.walls, np.asarray(b["walls"])) and np.array_equal(a.gates, np.asarray(b["gates"]))
+        assert a.start == tuple(b["start"]) and a.angle == b["angle"]
+    with pytest.raises(FileNotFoundError):
+        ppo_car_b200.load_track(os.path.join(tracks_dir, "nope.json"))

@@ -1,0 +1,187 @@
+"""GPU parity tests proper: everything goes through the C ABI (ppo_car_b200.VecCarEnv / Buffer ->
+libcarenv_b200.so) and is compared with (1) the golden trajectories recorded from the unmodified
+reference, (2) the float64 C oracle on the same seeded inputs, (3) size-independent properties at
+the full BASELINE sizes.  Integer outputs bit-exact, float outputs 1e-5 relative (tests/parity.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ppo_car_b200
+from oracle.c_oracle import COracleVecEnv
+from oracle.carenv_port import gae_port
+from tests.parity import assert_floats_close, assert_trajectory_matches
+
+pytestmark = pytest.mark.gpu
+GROUPS = ["const", "lap", "random", "fwd"]
+
+
+def _gpu_traj(out):
+    info = out["info"]
+    return dict(obs=out["obs"].cpu().numpy(), rew=out["reward"].cpu().numpy(), term=out["terminated"].cpu().numpy(),
+                trunc=out["truncated"].cpu().numpy(), gates_passed=info["gates_passed"].cpu().numpy(),
+                time_passed=info["time_passed"].cpu().numpy(), next_gate_index=info["next_gate_index"].cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["track", "big_track"])
+def test_golden_trajectories_from_the_reference(golden_dir, tracks_dir, name):
+    g = np.load(os.path.join(golden_dir, f"carenv_{name}.npz"))
+    path = os.path.join(tracks_dir, name + ".json")
+    for group in GROUPS:
+        acts = g[f"{group}_actions"]
+        env = ppo_car_b200.VecCarEnv(acts.shape[1], path)
+        obs0, _ = env.reset()
+        assert_floats_close(obs0.cpu().numpy(), np.broadcast_to(g["reset_obs"], obs0.shape), "reset obs")
+        out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
+        done = (g[f"{group}_term"] | g[f"{group}_trunc"]).astype(bool)
+        ref = dict(obs=np.where(done[..., None], g["reset_obs"], g[f"{group}_final_obs"]), rew=g[f"{group}_rew"],
+                   term=g[f"{group}_term"], trunc=g[f"{group}_trunc"], gates_passed=g[f"{group}_gates_passed"],
+                   time_passed=g[f"{group}_time_passed"], next_gate_index=g[f"{group}_next_gate_index"])
+        assert_trajectory_matches(_gpu_traj(out), ref, what=f"{name}/{group}")
+        if group == "lap":
+            assert int(out["info"]["lap"].sum()) == 1
+        env.close()
+
+
+@pytest.mark.parametrize("name,n_envs,biased", [("big_track", 4096, False), ("track", 4096, True), ("big_track", 24, False)])
+def test_random_rollout_matches_float64_oracle(tracks_dir, name, n_envs, biased):
+    """BASELINE configs 1/2 shape (24 x 1024) and a 4096-env case: same action tensor into both."""
+    T = 1024
+    rng = np.random.default_rng(11)
+    p = [.3, .02, .1, .1, .2, .2, .02, .02, .04] if biased else None
+    acts = rng.choice(9, size=(T, n_envs), p=p).astype(np.uint8)
+    path = os.path.join(tracks_dir, name + ".json")
+    ora = COracleVecEnv(n_envs, path, scan_all_gates=False)
+    ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    env = ppo_car_b200.VecCarEnv(n_envs, path)
+    env.reset()
+    out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
+    assert_trajectory_matches(_gpu_traj(out), ref, what=name)
+    counts = env.slow_path_counts()
+    assert sum(counts.values()) < 2e-3 * acts.size, counts
+
+
+def test_step_api_device_and_numpy_paths_agree_with_rollout(tracks_dir):
+    """step() with CUDA int64 actions (Categorical.sample dtype), with numpy actions, and the
+    multi-step rollout launch give identical results; reward_scaling and float flags work."""
+    path = os.path.join(tracks_dir, "big_track.json")
+    n, T = 257, 200                                  # ragged: not a multiple of the block size
+    rng = np.random.default_rng(5)
+    acts = rng.choice(9, size=(T, n), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04])
+    env_a = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1)
+    env_b = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1)
+    env_c = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1, float_flags=True)
+    oa, _ = env_a.reset()
+    env_b.reset(options={"track_path": path})
+    env_c.reset()
+    assert env_a.single_observation_space.shape == (18,) and env_a.single_action_space.n == 9
+    ref = env_c.rollout(torch.from_numpy(acts.astype(np.int32)).cuda(), store_info=True)
+    for t in range(T):
+        o1, r1, te1, tr1, i1 = env_a.step(torch.from_numpy(acts[t]).cuda())          # int64 on device
+        o2, r2, te2, tr2, i2 = env_b.step(acts[t])                                    # numpy in, numpy out
+        assert o1.dtype == torch.float32 and te1.dtype == torch.bool and r1.dtype == torch.float32
+        assert isinstance(o2, np.ndarray) and te2.dtype == np.bool_
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(te1.cpu().numpy(), te2) and np.array_equal(tr1.cpu().numpy(), tr2)
+        assert np.array_equal(o2, ref["obs"][t].cpu().numpy())
+        assert np.array_equal(r2, ref["reward"][t].cpu().numpy())
+        assert np.array_equal(te2.astype(np.float32), ref["terminated"][t].cpu().numpy())
+        assert np.array_equal(i2["gates_passed"], ref["info"]["gates_passed"][t].cpu().numpy())
+    assert ref["terminated"].sum() > 0
+    # state arrays agree after T single steps and after one T-step launch
+    assert torch.equal(env_a.pos, env_c.pos) and torch.equal(env_a.ints, env_c.ints)
+
+
+def test_full_size_properties_65536_envs(tracks_dir):
+    """BASELINE config 3 size (65,536 envs): properties that need no oracle.
+    Shard invariance (env i does not depend on how many envs share the launch), time counter
+    consistency, reward value set, reset observation on every done step, bounded observations."""
+    path = os.path.join(tracks_dir, "big_track.json")
+    n, T = 65536, 256
+    g = torch.Generator(device="cuda").manual_seed(0)
+    acts = torch.randint(0, 9, (T, n), generator=g, device="cuda", dtype=torch.uint8)
+    env = ppo_car_b200.VecCarEnv(n, path)
+    env.reset()
+    out = env.rollout(acts, store_info=True)
+    done = (out["terminated"] | out["truncated"]).bool()
+    assert not (out["terminated"] & out["truncated"]).any()
+    robs = torch.from_numpy(env.reset_observation).cuda()
+    assert torch.equal(out["obs"][done], robs.expand(int(done.sum()), 18))
+    tp = out["info"]["time_passed"]
+    prev = torch.cat([torch.zeros_like(tp[:1]), torch.where(done[:-1], torch.zeros_like(tp[:-1]), tp[:-1])])
+    assert torch.equal(tp, prev + 1)
+    vals = torch.unique(out["reward"]).cpu().numpy().astype(np.float64)
+    allowed = np.array([r for r in (0.0, 0.01, 1.0, 0.01 + 1.0, -3.0, 0.01 - 3.0, 1.0 - 3.0, (0.01 + 1.0) - 3.0)],
+                       np.float64).astype(np.float32)
+    assert set(vals.astype(np.float32)) <= set(allowed)
+    o = out["obs"]
+    assert (o[..., 6:] > 0).all() and (o[..., 6:] <= 1.0).all() and (o[..., 2:6].abs() <= 1.0).all()
+    # shard invariance: the first 1000 and the last 4097 envs replayed alone give the same traces
+    for lo, hi in ((0, 1000), (n - 4097, n)):
+        sub = ppo_car_b200.VecCarEnv(hi - lo, path)
+        sub.reset()
+        so = sub.rollout(acts[:, lo:hi].contiguous(), store_info=True)
+        assert torch.equal(so["obs"], out["obs"][:, lo:hi]) and torch.equal(so["reward"], out["reward"][:, lo:hi])
+        assert torch.equal(so["terminated"], out["terminated"][:, lo:hi])
+        assert torch.equal(so["info"]["gates_passed"], out["info"]["gates_passed"][:, lo:hi])
+    # and a 4096-env slice of it agrees with the float64 oracle
+    ora = COracleVecEnv(4096, path, scan_all_gates=False)
+    ora.reset()
+    ref = ora.rollout(acts[:, :4096].cpu().numpy(), want=("term", "trunc", "gates_passed"))
+    assert np.array_equal(out["terminated"][:, :4096].cpu().numpy(), ref["term"])
+    assert np.array_equal(out["info"]["gates_passed"][:, :4096].cpu().numpy(), ref["gates_passed"])
+
+
+@pytest.mark.parametrize("tag", ["small", "train", "wide"])
+def test_gae_golden_bit_exact(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "gae.npz"))
+    c = lambda k: torch.from_numpy(g[f"{tag}_{k}"]).cuda()
+    adv, ret = ppo_car_b200.gae_reverse_scan(c("rew"), c("val"), c("term"), c("trunc"), c("last_val"), c("last_term"),
+                                             c("last_trunc"))
+    assert np.array_equal(adv.cpu().numpy(), g[f"{tag}_adv"]) and np.array_equal(ret.cpu().numpy(), g[f"{tag}_ret"])
+
+
+def test_gae_buffer_api_and_full_size_bit_exact():
+    """Buffer drop-in at BASELINE config 3 size [1024, 65536] against the float32 port of lib/buffer.py."""
+    T, N = 1024, 65536
+    g = torch.Generator(device="cuda").manual_seed(1)
+    buf = ppo_car_b200.Buffer((18,), T, N, "cuda", gamma=0.99, gae_lambda=0.95)
+    with pytest.raises(AssertionError):
+        buf.calculate_advantages(torch.zeros(1, N).cuda(), torch.zeros(1, N).cuda(), torch.zeros(1, N).cuda())
+    buf.rew_buf.copy_(torch.rand((T, N), generator=g, device="cuda") * 1.4 - 0.3)
+    buf.val_buf.copy_(torch.randn((T, N), generator=g, device="cuda"))
+    buf.term_buf.copy_((torch.rand((T, N), generator=g, device="cuda") < 0.004).float())
+    buf.trunc_buf.copy_((torch.rand((T, N), generator=g, device="cuda") < 0.001).float())
+    buf.ptr = T
+    lv = torch.randn((1, N), generator=g, device="cuda")
+    lt = (torch.rand((1, N), generator=g, device="cuda") < 0.01).float()
+    lu = (torch.rand((1, N), generator=g, device="cuda") < 0.01).float()
+    adv, ret = buf.calculate_advantages(lv, lt, lu)
+    ra, rr = gae_port(buf.rew_buf.cpu().numpy(), buf.val_buf.cpu().numpy(), buf.term_buf.cpu().numpy(),
+                      buf.trunc_buf.cpu().numpy(), lv.cpu().numpy(), lt.cpu().numpy(), lu.cpu().numpy())
+    assert np.array_equal(adv.cpu().numpy(), ra) and np.array_equal(ret.cpu().numpy(), rr)
+    obs, act, val, logp = buf.get()
+    assert buf.ptr == 0 and obs.shape == (T, N, 18)
+
+
+def test_buffer_store_rows_from_env_step(tracks_dir):
+    """The train.py:173-195 loop shape: step -> store -> GAE, all on device."""
+    path = os.path.join(tracks_dir, "track.json")
+    n, T = 24, 64
+    env = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1, float_flags=True)
+    buf = ppo_car_b200.Buffer((18,), T, n, "cuda")
+    obs, _ = env.reset()
+    term = trunc = torch.zeros(n, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for _ in range(T):
+        a = torch.randint(0, 9, (n,), generator=g, device="cuda")
+        o = obs.clone()
+        obs, rew, nterm, ntrunc, _ = env.step(a)
+        buf.store(o, a, rew, torch.zeros(n, device="cuda"), term, trunc, torch.zeros(n, device="cuda"))
+        term, trunc = nterm.clone(), ntrunc.clone()
+    adv, ret = buf.calculate_advantages(torch.zeros(1, n).cuda(), term.reshape(1, -1), trunc.reshape(1, -1))
+    ra, rr = gae_port(buf.rew_buf.cpu().numpy(), buf.val_buf.cpu().numpy(), buf.term_buf.cpu().numpy(),
+                      buf.trunc_buf.cpu().numpy(), np.zeros(n, np.float32), term.cpu().numpy(), trunc.cpu().numpy())
+    assert np.array_equal(adv.cpu().numpy(), ra) and np.array_equal(ret.cpu().numpy(), rr)

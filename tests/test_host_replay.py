@@ -1,0 +1,61 @@
+"""CPU-only: replay the kernel's arithmetic (float32 fast path + guard bands + float64 fallbacks,
+compiled for the host from the very same header the GPU kernel uses) against the golden
+trajectories of the reference and against the float64 C oracle.  This is what lets the integer
+traces be checked at scale without a GPU; the -m gpu tests repeat it on the device."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.c_oracle import COracleVecEnv
+from tests.emul_util import emul_rollout
+from tests.parity import assert_floats_close, assert_trajectory_matches
+
+GROUPS = ["const", "lap", "random", "fwd"]
+
+
+@pytest.mark.parametrize("name", ["track", "big_track"])
+def test_kernel_arithmetic_replays_reference_golden(golden_dir, tracks_dir, name):
+    g = np.load(os.path.join(golden_dir, f"carenv_{name}.npz"))
+    for group in GROUPS:
+        e = emul_rollout(os.path.join(tracks_dir, name + ".json"), g[f"{group}_actions"])
+        assert_floats_close(e["reset_obs"], g["reset_obs"], "reset obs")
+        done = (g[f"{group}_term"] | g[f"{group}_trunc"]).astype(bool)
+        ref = dict(obs=np.where(done[..., None], g["reset_obs"], g[f"{group}_final_obs"]), rew=g[f"{group}_rew"],
+                   term=g[f"{group}_term"], trunc=g[f"{group}_trunc"], gates_passed=g[f"{group}_gates_passed"],
+                   time_passed=g[f"{group}_time_passed"], next_gate_index=g[f"{group}_next_gate_index"])
+        got = dict(obs=e["obs"], rew=e["rew"], term=e["term"], trunc=e["trunc"], gates_passed=e["info"][..., 0],
+                   time_passed=e["info"][..., 1], next_gate_index=e["info"][..., 2])
+        assert_trajectory_matches(got, ref, what=f"{name}/{group}")
+        if group == "lap":
+            assert (e["info"][..., 3] >> 1).sum() == 1          # exactly one lap (+10) event
+
+
+@pytest.mark.parametrize("name,n_envs,biased", [("big_track", 2048, False), ("track", 2048, True)])
+def test_kernel_arithmetic_matches_oracle_at_scale(tracks_dir, name, n_envs, biased):
+    T = 512
+    rng = np.random.default_rng(7)
+    p = [.3, .02, .1, .1, .2, .2, .02, .02, .04] if biased else None
+    acts = rng.choice(9, size=(T, n_envs), p=p).astype(np.uint8)
+    path = os.path.join(tracks_dir, name + ".json")
+    ora = COracleVecEnv(n_envs, path, scan_all_gates=False)
+    ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    e = emul_rollout(path, acts)
+    got = dict(obs=e["obs"], rew=e["rew"], term=e["term"], trunc=e["trunc"], gates_passed=e["info"][..., 0],
+               time_passed=e["info"][..., 1], next_gate_index=e["info"][..., 2])
+    assert_trajectory_matches(got, ref, what=name)
+    assert ref["term"].sum() > 1000
+    # the float64 fallback must stay rare (it is a correctness device, not the main path)
+    assert e["stats"].sum() < 2e-3 * acts.size
+
+
+def test_reward_scaling_is_float32_of_float64_product(tracks_dir):
+    rng = np.random.default_rng(3)
+    acts = rng.choice(9, size=(300, 64), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04]).astype(np.uint8)
+    path = os.path.join(tracks_dir, "big_track.json")
+    a, b = emul_rollout(path, acts, reward_scale=1.0), emul_rollout(path, acts, reward_scale=0.1)
+    # TransformReward multiplies the float64 reward (train.py:65); Buffer stores float32 (lib/buffer.py:14)
+    r64 = np.select([np.isclose(a["rew"], v) for v in (0.01, 1.0, 1.01, -3.0, -2.99, -2.0, -1.99)],
+                    [0.01, 1.0, 0.01 + 1.0, -3.0, 0.01 - 3.0, 1.0 - 3.0, (0.01 + 1.0) - 3.0], 0.0)
+    assert np.array_equal(b["rew"], (r64 * 0.1).astype(np.float32))

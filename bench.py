@@ -7,9 +7,11 @@
 
 Workload (config.workload): BASELINE.json configs[3] — tracks/big_track.json, 1,048,576
 environments in total, i.i.d. uniform random actions, sharded over the N ranks by contiguous env
-ranges with no data-path collective (strong scaling: the total is fixed).  One timed "step" is one
-`carenv_rollout` launch per rank that advances every local environment by `chunk` CarEnv steps and
-writes the observation, reward and both flags of every one of them to HBM.
+ranges with no data-path collective (strong scaling: the total is fixed).  One timed "step" is
+`launches` back-to-back `carenv_rollout` launches per rank, each advancing every local environment
+by `chunk` CarEnv steps and writing the observation, reward and both flags of every one of them to
+HBM (default 8 x 32 = 256 env steps per environment per bench step, so that K = 20 steps keep the
+GPU busy for about half a second and the clock samples are taken under load).
 
   value     env-steps/s with actions already resident in HBM (device timed, CUDA events, max over ranks)
   e2e       env-steps/s through the reference-facing API VecCarEnv.step(numpy actions) -> numpy
@@ -232,8 +234,12 @@ def run_ours(args):
     term = torch.empty((chunk, n), dtype=torch.uint8, device=dev)
     trunc = torch.empty((chunk, n), dtype=torch.uint8, device=dev)
 
+    launches = args.launches
+
     def one_step(i):
-        env.rollout(acts[i % n_act_bufs], obs_out=obs, reward_out=rew, term_out=term, trunc_out=trunc)
+        for j in range(launches):
+            env.rollout(acts[(i * launches + j) % n_act_bufs], obs_out=obs, reward_out=rew, term_out=term,
+                        trunc_out=trunc)
 
     for i in range(args.warmup):
         one_step(i)
@@ -256,7 +262,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
-    value = args.steps * chunk * total / (dev_ms_max * 1e-3)
+    value = args.steps * launches * chunk * total / (dev_ms_max * 1e-3)
     slow = env.slow_path_counts()
 
     # ---- e2e: reference-facing API with HOST buffers (numpy in, numpy out), one env step per call
@@ -307,7 +313,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         ffma_tflops = blocks * 256 * iters * 64 * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
-        launch_ms = sum(per_launch_ms) / len(per_launch_ms)      # rank 0's average launch duration
+        launch_ms = sum(per_launch_ms) / len(per_launch_ms) / launches   # rank 0's average launch duration
         steps_per_launch = chunk * n
         achieved_tflops = steps_per_launch * FLOP_PER_ENV_STEP / (launch_ms * 1e-3) / 1e12
         bytes_per_launch = steps_per_launch * BYTES_PER_ENV_STEP + n * 2 * STATE_BYTES
@@ -318,16 +324,18 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 ray casting, f64 state", "data": "synthetic",
             "config": {"workload": f"tracks/{TRACK}.json, {total} envs total ({n} per GPU), uniform random actions "
-                                   f"resident in HBM, same-step autoreset, {chunk} env steps per launch; every step "
-                                   "writes obs[18] f32 + reward f32 + terminated/truncated u8 per env",
-                       "envs_total": total, "envs_per_gpu": n, "steps_per_launch": chunk, "sharding": f"env{world}",
+                                   f"resident in HBM, same-step autoreset, {launches} launches x {chunk} env steps per "
+                                   "bench step; every env step writes obs[18] f32 + reward f32 + terminated/truncated "
+                                   "u8 per env",
+                       "envs_total": total, "envs_per_gpu": n, "steps_per_launch": chunk,
+                       "launches_per_step": launches, "sharding": f"env{world}",
                        "cache": f"outputs per launch {obs.numel() * 4 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},
             "wall_s": t_wall,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "VecCarEnv.step(numpy int64 actions) -> numpy obs/reward/terminated/truncated/info",
                     "steps": e_steps},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * launches,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_nominal, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_nominal, "traffic": None,
                          "kernel": "k_rollout<uint8,uint8>", "launch_ms": launch_ms,
@@ -355,7 +363,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=TOTAL_ENVS, help="total environments over all GPUs")
-    ap.add_argument("--chunk", type=int, default=16, help="env steps per rollout launch")
+    ap.add_argument("--chunk", type=int, default=32, help="env steps per rollout launch")
+    ap.add_argument("--launches", type=int, default=8, help="rollout launches per timed bench step")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

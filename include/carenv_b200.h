@@ -91,6 +91,10 @@ int carenv_rollout(void *handle, int n_envs, int n_steps, double *pos, double *v
                    const void *actions, int action_dtype, double reward_scale, float *obs_out, float *reward_out,
                    void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream);
 
+/* Tuning / test options.  "force_generic" = 1 runs the generic segment loop even for tracks that have
+ * a fully unrolled kernel instantiation (the two produce identical results). */
+int carenv_set_option(void *handle, const char *name, int value);
+
 /* Slow-path counters since the last reset of the counters: [0] lines re-evaluated in float64
  * because an endpoint was within eps of a ray line, [1] rays re-evaluated because a cardinal
  * distance was within the band around 10 px, [2] gate tests re-evaluated, [3] distances below

@@ -12,7 +12,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libcarenv_b200.so")
+LIB_PATH = os.environ.get("CARENV_LIB") or os.path.join(_PKG, "libcarenv_b200.so")   # override: kernel experiments
 SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("carenv_kernels.cu", "carenv_core.cuh", "carenv_tables.h")]
 HEADER = os.path.join(ROOT, "include", "carenv_b200.h")
 
@@ -65,10 +65,11 @@ def lib():
     L.carenv_step.argtypes = [vp, i32, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp, i32, vp, vp]
     L.carenv_rollout.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp, i32, vp, vp]
     L.carenv_stats.argtypes = [vp, vp, i32]
+    L.carenv_set_option.argtypes = [vp, C.c_char_p, i32]
     L.gae_reverse_scan.argtypes = [vp] * 9 + [i32, i32, f64, f64, vp]
     L.carenv_bench_ffma.argtypes = [i32, i32, vp, vp]
     for name in ("carenv_create", "carenv_destroy", "carenv_reset_obs", "carenv_reset", "carenv_step",
-                 "carenv_rollout", "carenv_stats", "gae_reverse_scan", "carenv_bench_ffma"):
+                 "carenv_rollout", "carenv_stats", "gae_reverse_scan", "carenv_bench_ffma", "carenv_set_option"):
         getattr(L, name).restype = i32
     if L.carenv_abi_version() != 1:
         raise CarEnvError("libcarenv_b200.so ABI version mismatch; rebuild")

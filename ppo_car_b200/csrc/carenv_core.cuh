@@ -50,11 +50,9 @@ constexpr int kTimeLimit = 1000;   // lib/car_env.py:491
 struct F2 { float x, y; };
 struct D2 { double x, y; };
 
-// One wall segment A->B.  Endpoints are split hi+lo so that (P - pos) can be formed in
-// float32 with a relative (not absolute) rounding error.
+// One wall segment A->B in float32 (endpoints rounded from float64; they only feed sign tests).
 struct SegF {
-    float ahx, ahy, alx, aly;
-    float bhx, bhy, blx, bly;
+    float ahx, ahy, bhx, bhy;
     float ex, ey;          // B - A rounded from float64
     int chain_start;       // 1: A is not the previous segment's B
     int pad;
@@ -69,6 +67,9 @@ struct TrackParams {
     float coll_band;    // relative half-width of the band around d == 10
     float tiny_d;       // distances below this are re-evaluated (sign of u uncertain)
     float gate_band;    // gate margin band, in units of the gate length
+    float tiny_un;      // |cross(e, A')| below this: every line is re-evaluated
+    int unroll;         // largest U in {4, 2, 1} such that n_seg and every polyline start are multiples of U
+    int pad2[2];
     double start_x, start_y;
     float reset_obs[kObsDim];
     float pad1[2];
@@ -216,53 +217,98 @@ CE_HD void integrate(EnvState &s, int thrust, int k_pre, const Tables &T) {
 }
 
 // ---- the 12 ray distances and the wall-collision decision -------------------------------------
+struct WallAcc {
+    float c[3], sn[3];      // directions of lines 0..2 (heading + 0/30/60 deg); lines 3..5 are these rotated by 90 deg
+    float phx, phy;         // float32(pos)
+    float Rp[6], Rm[6];     // max of r = 1/u over hits with u > 0 (ray l) / min over hits with u < 0 (ray l+6)
+    float gq[6];            // min |q| per line  -> hit/miss guard
+    float gu;               // min |cross(e, A')| -> sign-of-u guard
+    float qa[6];            // q of the previous endpoint on each line
+};
+
+// q of one endpoint on the six lines.  Only the SIGN of q is used (and |q| for the guard), so the
+// endpoint is localised with a single float32 subtraction: |dq| <= 6.1e-4 px for |P - pos| <= 1500 px
+// (rounding of P, of pos, of the difference, of the two products and of the direction), below eps_q.
+CE_HD void wall_point(const WallAcc &w, float hx, float hy, float q[6]) {
+    const float x = fsub(hx, w.phx), y = fsub(hy, w.phy);
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        q[l] = ffma(x, w.sn[l], -fmul(y, w.c[l]));        // cross(P', d_l)
+        q[l + 3] = ffma(x, w.c[l], fmul(y, w.sn[l]));     // cross(P', rot90 d_l) = dot(P', d_l)
+    }
+}
+
+// Start of a polyline: q of its first point (the previous segment's end point does not carry over).
+CE_HD void wall_chain_start(WallAcc &w, const SegF &f) {
+    wall_point(w, f.ahx, f.ahy, w.qa);
+#pragma unroll
+    for (int l = 0; l < 6; ++l) w.gq[l] = fminf(w.gq[l], fabsf(w.qa[l]));
+}
+
+// One wall segment against the six lines.
+// GUARD: 1 = fold |q| of this segment's end point into the guard, 2 = fold |q| of BOTH end points
+// (one 3-input min per line covers two polyline points), 0 = leave it to the next segment's GUARD 2.
+template <int GUARD>
+CE_HD void wall_segment(WallAcc &w, const SegF &f, const SegD &g, double px, double py) {
+    float qb[6];
+    wall_point(w, f.bhx, f.bhy, qb);
+    // cross(e, A - pos) in float64 (two FMAs on the FP64 pipe), rounded once, one float32 reciprocal
+    const float un = (float)dfma(g.ey, px, dfma(-g.ex, py, g.K));
+    const float inv = frcp(un);
+    w.gu = fminf(w.gu, fabsf(un));
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        // cross(e, d_l) / cross(e, A') = 1/u.  (Pre-scaling e by inv would save a multiply per test but
+        // measurably costs accuracy: 1.2e-5 instead of 1.6e-6 worst relative distance error.)
+        const float r0 = fmul(ffma(f.ex, w.sn[l], -fmul(f.ey, w.c[l])), inv);
+        const float r3 = fmul(ffma(f.ex, w.c[l], fmul(f.ey, w.sn[l])), inv);
+        if (fmul(w.qa[l], qb[l]) < 0.0f) { w.Rp[l] = fmaxf(w.Rp[l], r0); w.Rm[l] = fminf(w.Rm[l], r0); }
+        if (fmul(w.qa[l + 3], qb[l + 3]) < 0.0f) { w.Rp[l + 3] = fmaxf(w.Rp[l + 3], r3); w.Rm[l + 3] = fminf(w.Rm[l + 3], r3); }
+    }
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+        if (GUARD == 1) w.gq[l] = fminf(w.gq[l], fabsf(qb[l]));
+        if (GUARD == 2) w.gq[l] = fminf(fminf(w.gq[l], fabsf(w.qa[l])), fabsf(qb[l]));
+        w.qa[l] = qb[l];
+    }
+}
+
 // dist[i] (pixels, float32) for ray i = heading + 30*i degrees; returns destroyed.
+// U = segments per loop iteration.  U > 1 requires (checked on the host, TrackParams::unroll) that
+// n_seg and every polyline start are multiples of U; the body is then U segments of straight-line
+// code (about 1.5 KB each) — small enough to stay in the instruction cache, which a full unroll of
+// 24 segments is not (measured: 1.5 "no instruction" stalls per issue and a slower kernel).
+template <int U>
 CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, float dist[kNumRays],
                       unsigned long long *stats) {
-    const float phx = (float)s.px, phy = (float)s.py;
-    const float plx = (float)dsub(s.px, (double)phx), ply = (float)dsub(s.py, (double)phy);
-    float c[3], sn[3];
+    WallAcc w;
+    w.phx = (float)s.px; w.phy = (float)s.py;
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
         const F2 d = T.trig32[wrap72(s.k + 6 * l)];
-        c[l] = d.x; sn[l] = d.y;
+        w.c[l] = d.x; w.sn[l] = d.y;
     }
     const float R0 = 1.0e-3f;           // 1/1000: "no hit" (lib/car_env.py:198)
-    float Rp[6], Rm[6], gq[6], qa[6];
 #pragma unroll
-    for (int l = 0; l < 6; ++l) { Rp[l] = R0; Rm[l] = -R0; gq[l] = 1.0e30f; qa[l] = 0.0f; }
+    for (int l = 0; l < 6; ++l) { w.Rp[l] = R0; w.Rm[l] = -R0; w.gq[l] = 1.0e30f; w.qa[l] = 0.0f; }
+    w.gu = 1.0e30f;
 
-#pragma unroll 2
-    for (int j = 0; j < P.n_seg; ++j) {
-        const SegF f = P.segf[j];
-        const SegD g = P.segd[j];
-        if (f.chain_start) {
-            const float ax = fadd(fsub(f.ahx, phx), fsub(f.alx, plx));
-            const float ay = fadd(fsub(f.ahy, phy), fsub(f.aly, ply));
+    if (U > 1) {
+#pragma unroll 1
+        for (int j0 = 0; j0 < P.n_seg; j0 += U) {
+            if (P.segf[j0].chain_start) wall_chain_start(w, P.segf[j0]);
 #pragma unroll
-            for (int l = 0; l < 3; ++l) {
-                qa[l] = ffma(ax, sn[l], -fmul(ay, c[l]));
-                qa[l + 3] = ffma(ax, c[l], fmul(ay, sn[l]));
-                gq[l] = fminf(gq[l], fabsf(qa[l]));
-                gq[l + 3] = fminf(gq[l + 3], fabsf(qa[l + 3]));
+            for (int u = 0; u < U; ++u) {
+                if (u % 2 == 1) wall_segment<2>(w, P.segf[j0 + u], P.segd[j0 + u], s.px, s.py);
+                else if (u == U - 1) wall_segment<1>(w, P.segf[j0 + u], P.segd[j0 + u], s.px, s.py);
+                else wall_segment<0>(w, P.segf[j0 + u], P.segd[j0 + u], s.px, s.py);
             }
         }
-        const float bx = fadd(fsub(f.bhx, phx), fsub(f.blx, plx));
-        const float by = fadd(fsub(f.bhy, phy), fsub(f.bly, ply));
-        // cross(e, A - pos) in float64 (two FMAs on the FP64 pipe), then one float32 reciprocal
-        const double un64 = dfma(g.ey, s.px, dfma(-g.ex, s.py, g.K));
-        const float inv = frcp((float)un64);
-#pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            const float qb0 = ffma(bx, sn[l], -fmul(by, c[l]));
-            const float qb3 = ffma(bx, c[l], fmul(by, sn[l]));
-            const float r0 = fmul(ffma(f.ex, sn[l], -fmul(f.ey, c[l])), inv);   // cross(e,d)/cross(e,A')
-            const float r3 = fmul(ffma(f.ex, c[l], fmul(f.ey, sn[l])), inv);
-            if (fmul(qa[l], qb0) < 0.0f) { Rp[l] = fmaxf(Rp[l], r0); Rm[l] = fminf(Rm[l], r0); }
-            if (fmul(qa[l + 3], qb3) < 0.0f) { Rp[l + 3] = fmaxf(Rp[l + 3], r3); Rm[l + 3] = fminf(Rm[l + 3], r3); }
-            gq[l] = fminf(gq[l], fabsf(qb0));
-            gq[l + 3] = fminf(gq[l + 3], fabsf(qb3));
-            qa[l] = qb0; qa[l + 3] = qb3;
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < P.n_seg; ++j) {
+            if (P.segf[j].chain_start) wall_chain_start(w, P.segf[j]);
+            wall_segment<1>(w, P.segf[j], P.segd[j], s.px, s.py);
         }
     }
 
@@ -270,20 +316,22 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
     const float r_tiny = frcp(P.tiny_d);
     const float r_coll = 0.1f;                    // d < 10  <=>  1/d > 0.1
     const float r_band = fmul(r_coll, P.coll_band);
+    const bool redo_all = w.gu < P.tiny_un;       // car (numerically) on a wall line: sign of u unknown
     bool destroyed = false;
 #pragma unroll
     for (int l = 0; l < 6; ++l) {
         const bool cardinal = (l == 0 || l == 3);
-        bool redo = gq[l] < P.eps_q;
+        bool redo = redo_all || (w.gq[l] < P.eps_q);
         if (redo) stat_add(stats, kStatLine);
-        if (!redo && (Rp[l] > r_tiny || Rm[l] < -r_tiny)) { redo = true; stat_add(stats, kStatTiny); }
-        if (!redo && cardinal && (fabsf(fsub(Rp[l], r_coll)) < r_band || fabsf(fadd(Rm[l], r_coll)) < r_band)) {
+        if (!redo && (w.Rp[l] > r_tiny || w.Rm[l] < -r_tiny)) { redo = true; stat_add(stats, kStatTiny); }
+        if (!redo && cardinal &&
+            (fabsf(fsub(w.Rp[l], r_coll)) < r_band || fabsf(fadd(w.Rm[l], r_coll)) < r_band)) {
             redo = true; stat_add(stats, kStatBand);
         }
         if (!redo) {
-            dist[l] = Rp[l] > R0 ? frcp(Rp[l]) : 1000.0f;
-            dist[l + 6] = Rm[l] < -R0 ? -frcp(Rm[l]) : 1000.0f;
-            if (cardinal) destroyed = destroyed || (Rp[l] > r_coll) || (Rm[l] < -r_coll);
+            dist[l] = w.Rp[l] > R0 ? frcp(w.Rp[l]) : 1000.0f;
+            dist[l + 6] = w.Rm[l] < -R0 ? -frcp(w.Rm[l]) : 1000.0f;
+            if (cardinal) destroyed = destroyed || (w.Rp[l] > r_coll) || (w.Rm[l] < -r_coll);
         } else {
             const D2 d0 = T.trig64[wrap72(s.k + 6 * l)], d1 = T.trig64[wrap72(s.k + 6 * l + 36)];
             const double e0 = exact_ray_distance(s.px, s.py, d0.x, d0.y, T.walls64, P.n_seg);
@@ -296,6 +344,7 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
 }
 
 // ---- one CarEnv.step with same-step autoreset --------------------------------------------------
+template <int U>
 CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackParams &P, const Tables &T,
                     StepResult &o, unsigned long long *stats) {
     int thrust, turn;
@@ -316,7 +365,7 @@ CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackPar
     integrate(s, thrust, k_pre, T);
 
     float dist[kNumRays];
-    bool destroyed = cast_walls(s, P, T, dist, stats);
+    bool destroyed = cast_walls<U>(s, P, T, dist, stats);
     destroyed = destroyed || (P.start_destroyed != 0);
     s.t += 1;
     o.terminated = 0; o.truncated = 0;

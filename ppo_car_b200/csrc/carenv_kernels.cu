@@ -46,6 +46,7 @@ struct Handle {
     Tables dev;               // device pointers into d_blob
     unsigned long long *d_stats;
     size_t smem_bytes;
+    int force_generic;        // test hook: run the generic (not unrolled) kernel
 };
 
 struct DeviceGuard {
@@ -89,8 +90,11 @@ __device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, uns
     return Tables{s_trig32, s_trig64, s_acc64, s_gates, G.walls64};
 }
 
-template <typename ActT, typename FlagT>
-__global__ void __launch_bounds__(kBlock)
+#ifndef CARENV_MIN_BLOCKS
+#define CARENV_MIN_BLOCKS 4
+#endif
+template <typename ActT, typename FlagT, int U>
+__global__ void __launch_bounds__(kBlock, CARENV_MIN_BLOCKS)
 k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int n_steps, double2 *__restrict__ pos,
           double2 *__restrict__ vel, int4 *__restrict__ ints, const ActT *__restrict__ actions, double reward_scale,
           float *__restrict__ obs_out, float *__restrict__ rew_out, FlagT *__restrict__ term_out,
@@ -111,7 +115,7 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
         const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
         const int a = (int)actions[idx];
         StepResult o;
-        env_step(s, a, reward_scale, P, T, o, stats);
+        env_step<U>(s, a, reward_scale, P, T, o, stats);
         if (obs_out) {
             float2 *dst = reinterpret_cast<float2 *>(obs_out + idx * kObsDim);
 #pragma unroll
@@ -208,11 +212,11 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
     if (sum == 12345.678f) out[0] = sum;   // keeps the chains alive without storing
 }
 
-template <typename ActT, typename FlagT>
-int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints, const void *actions,
+template <typename ActT, typename FlagT, int U>
+int launch_rollout_t(Handle *h, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints, const void *actions,
                    double reward_scale, float *obs_out, float *reward_out, void *term_out, void *trunc_out,
                    int32_t *info_out, cudaStream_t stream) {
-    auto kern = k_rollout<ActT, FlagT>;
+    auto kern = k_rollout<ActT, FlagT, U>;
     if (h->smem_bytes > 48 * 1024)
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     const int grid = (n_envs + kBlock - 1) / kBlock;
@@ -223,6 +227,19 @@ int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel,
         h->d_stats);
     CU(cudaGetLastError());
     return 0;
+}
+
+// Segment-loop unrolling is chosen per track (TrackParams::unroll); all variants give identical results.
+template <typename ActT, typename FlagT>
+int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints, const void *actions,
+                   double reward_scale, float *obs_out, float *reward_out, void *term_out, void *trunc_out,
+                   int32_t *info_out, cudaStream_t stream) {
+    const int U = h->force_generic ? 1 : h->host.P.unroll;
+#define ARGS h, n_envs, n_steps, pos, vel, ints, actions, reward_scale, obs_out, reward_out, term_out, trunc_out, info_out, stream
+    if (U == 4) return launch_rollout_t<ActT, FlagT, 4>(ARGS);
+    if (U == 2) return launch_rollout_t<ActT, FlagT, 2>(ARGS);
+    return launch_rollout_t<ActT, FlagT, 1>(ARGS);
+#undef ARGS
 }
 
 int dispatch_rollout(void *handle, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints,
@@ -271,7 +288,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -353,6 +370,13 @@ int carenv_rollout(void *handle, int n_envs, int n_steps, double *pos, double *v
                    void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream) {
     return dispatch_rollout(handle, n_envs, n_steps, pos, vel, ints, actions, action_dtype, reward_scale, obs_out,
                             reward_out, term_out, trunc_out, flag_dtype, info_out, stream);
+}
+
+int carenv_set_option(void *handle, const char *name, int value) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !name) return fail(CARENV_E_INVAL, "null argument");
+    if (std::string(name) == "force_generic") { h->force_generic = value ? 1 : 0; return 0; }
+    return fail(CARENV_E_INVAL, std::string("unknown option ") + name);
 }
 
 int carenv_stats(void *handle, unsigned long long out[4], int reset_counters) {

@@ -22,11 +22,6 @@ struct HostTrack {
     Tables tables() const { return Tables{trig32.data(), trig64.data(), acc64.data(), gates.data(), walls64.data()}; }
 };
 
-inline void split_hi_lo(double v, float &hi, float &lo) {
-    hi = (float)v;
-    lo = (float)(v - (double)hi);
-}
-
 // returns 0 on success, <0 on invalid input
 inline int build_host_track(const double *walls, int n_walls, const double *gates, int n_gates,
                             double sx, double sy, double angle_deg, HostTrack &H) {
@@ -51,8 +46,7 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
     for (int j = 0; j < n_walls; ++j) {
         const double ax = walls[4 * j], ay = walls[4 * j + 1], bx = walls[4 * j + 2], by = walls[4 * j + 3];
         SegF &f = P.segf[j];
-        split_hi_lo(ax, f.ahx, f.alx); split_hi_lo(ay, f.ahy, f.aly);
-        split_hi_lo(bx, f.bhx, f.blx); split_hi_lo(by, f.bhy, f.bly);
+        f.ahx = (float)ax; f.ahy = (float)ay; f.bhx = (float)bx; f.bhy = (float)by;
         const double ex = bx - ax, ey = by - ay;
         f.ex = (float)ex; f.ey = (float)ey;
         f.chain_start = (j == 0 || walls[4 * j - 2] != ax || walls[4 * j - 1] != ay) ? 1 : 0;
@@ -74,11 +68,20 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
     }
 
     // guard bands: bounds on the float32 error of q, r and the gate margin
-    P.eps_q = 1.0e-3f;      // |dq| <= 5.3 * 2^-24 * |P - pos| <= 4.7e-4 px for |P - pos| <= 1500 px
-    const double rel_r = 2.5e-7 / min_sin + 3.0e-7;   // relative error of r = cross(e,d) / cross(e,A')
-    P.coll_band = (float)fmax(1.0e-3, 4.0 * rel_r);
+    P.eps_q = 1.5e-3f;      // |dq| <= 6.1e-4 px for |P - pos| <= 1500 px (see wall_point)
+    const double rel_r = 4.0e-7 / min_sin + 3.0e-7;   // relative error of r = cross(e,d) / cross(e,A')
+    P.coll_band = (float)fmax(2.0e-4, 4.0 * rel_r);
     P.tiny_d = 1.0e-2f;
     P.gate_band = 2.0e-3f;
+    P.tiny_un = 1.0e-3f;    // float64 error of cross(e, A - pos) is ~1e-10: relative error < 1e-7 above this
+    // loop unrolling the track allows (see cast_walls)
+    P.unroll = 1;
+    for (int U = 4; U >= 2; U /= 2) {
+        bool ok = (n_walls % U == 0);
+        for (int j = 0; j < n_walls && ok; ++j)
+            if (P.segf[j].chain_start && j % U != 0) ok = false;
+        if (ok) { P.unroll = U; break; }
+    }
 
     const Tables T = H.tables();
     P.start_destroyed = reset_observation(P, T, P.reset_obs) ? 1 : 0;

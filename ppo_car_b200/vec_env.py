@@ -236,6 +236,9 @@ class VecCarEnv:
             out["info"] = self._info_dict(info_out)
         return out
 
+    def set_option(self, name: str, value: int) -> None:
+        _lib.check(self._L.carenv_set_option(self._handle, name.encode(), int(value)), "carenv_set_option")
+
     def slow_path_counts(self, reset: bool = True) -> dict:
         """How often the float64 re-evaluation ran since the last call (synchronises)."""
         out = (C.c_ulonglong * 4)()

@@ -25,7 +25,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def emul_rollout(track_path, actions, reward_scale=1.0, threads=None):
+def emul_rollout(track_path, actions, reward_scale=1.0, threads=None, unrolled=True):
     """Replay [T,N] actions from reset through the host build of the kernel arithmetic."""
     L = lib()
     tr = load_track(track_path)
@@ -42,7 +42,7 @@ def emul_rollout(track_path, actions, reward_scale=1.0, threads=None):
     def run(i):
         return L.emul_rollout(_p(walls), len(walls), _p(gates), len(gates), C.c_double(tr.start[0]),
                               C.c_double(tr.start[1]), C.c_double(tr.angle), N, int(edges[i]), int(edges[i + 1]), T,
-                              _p(a), C.c_double(reward_scale), _p(pv), _p(si), 1, _p(out["reset_obs"]), _p(out["obs"]),
+                              _p(a), C.c_double(reward_scale), _p(pv), _p(si), 1, int(unrolled), _p(out["reset_obs"]), _p(out["obs"]),
                               _p(out["rew"]), _p(out["term"]), _p(out["trunc"]), _p(out["info"]), _p(out["stats"]))
 
     with ThreadPoolExecutor(threads) as ex:

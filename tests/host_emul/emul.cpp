@@ -10,7 +10,7 @@ using namespace carenv;
 
 extern "C" int emul_rollout(const double *walls, int n_walls, const double *gates, int n_gates, double sx, double sy,
                             double angle, int n_envs, int env_lo, int env_hi, int T, const uint8_t *actions,
-                            double reward_scale, double *state_pv, int32_t *state_i, int do_reset, float *reset_obs,
+                            double reward_scale, double *state_pv, int32_t *state_i, int do_reset, int unrolled, float *reset_obs,
                             float *obs, float *rew, uint8_t *term, uint8_t *trunc, int32_t *info,
                             unsigned long long *stats) {
     HostTrack H;
@@ -28,7 +28,10 @@ extern "C" int emul_rollout(const double *walls, int n_walls, const double *gate
         for (int t = 0; t < T; ++t) {
             const size_t k = (size_t)t * n_envs + e;
             StepResult o;
-            env_step(s, actions[k], reward_scale, H.P, Tb, o, stats);
+            const int U = unrolled ? H.P.unroll : 1;
+            if (U == 4) env_step<4>(s, actions[k], reward_scale, H.P, Tb, o, stats);
+            else if (U == 2) env_step<2>(s, actions[k], reward_scale, H.P, Tb, o, stats);
+            else env_step<1>(s, actions[k], reward_scale, H.P, Tb, o, stats);
             if (obs) for (int i = 0; i < kObsDim; ++i) obs[k * kObsDim + i] = o.obs[i];
             if (rew) rew[k] = o.reward;
             if (term) term[k] = (uint8_t)o.terminated;

@@ -135,17 +135,46 @@ CE_HD float frcp(float x) { return 1.0f / x; }
 CE_HD void stat_add(unsigned long long *s, int i) { if (s) __atomic_fetch_add(s + i, 1ULL, __ATOMIC_RELAXED); }
 #endif
 
+// ---- packed pairs of float32 (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE operations per issue slot) ----
+#if defined(__CUDA_ARCH__)
+typedef float2 P2;
+CE_HD P2 p2(float x, float y) { return make_float2(x, y); }
+CE_HD P2 pfma(P2 a, P2 b, P2 c) { return __ffma2_rn(a, b, c); }
+CE_HD P2 pmul(P2 a, P2 b) { return __fmul2_rn(a, b); }
+CE_HD P2 padd(P2 a, P2 b) { return __fadd2_rn(a, b); }
+CE_HD float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+CE_HD float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+#else
+struct P2 { float x, y; };
+CE_HD P2 p2(float x, float y) { P2 r; r.x = x; r.y = y; return r; }
+CE_HD P2 pfma(P2 a, P2 b, P2 c) { return p2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+CE_HD P2 pmul(P2 a, P2 b) { return p2(a.x * b.x, a.y * b.y); }
+CE_HD P2 padd(P2 a, P2 b) { return p2(a.x + b.x, a.y + b.y); }
+CE_HD float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+CE_HD float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+#endif
+CE_HD float neg_mask(float w) { return w < 0.0f ? 1.0f : 0.0f; }   // FSET.BF.LT
+
 CE_HD int wrap72(int k) { return k >= kHeadings ? k - kHeadings : (k < 0 ? k + kHeadings : k); }
 
 // ---- literal float64 evaluation (the reference's formulas, lib/car_env.py:155-213) ----------
+// The hit test is evaluated without dividing: for correctly rounded division fl(a/b) > 0 <=> a/b > 0 and
+// fl(a/b) < 1 <=> |a| < |b|, so "0 < t < 1 and u > 0" on the reference's rounded quotients is decided by
+// the signs and magnitudes of the very same numerators and denominator.  t itself (one division) is only
+// formed for an actual hit, where the reference needs it for the hit point.
 CE_HD bool exact_cast(double ox, double oy, double dx, double dy, const double *seg, double &dist) {
     const double x1 = seg[0], y1 = seg[1], x2 = seg[2], y2 = seg[3];
     const double x3 = ox, y3 = oy, x4 = dadd(ox, dx), y4 = dadd(oy, dy);
     const double den = dsub(dmul(dsub(x1, x2), dsub(y3, y4)), dmul(dsub(y1, y2), dsub(x3, x4)));
     if (den == 0) return false;
-    const double t = dsub(dmul(dsub(x1, x3), dsub(y3, y4)), dmul(dsub(y1, y3), dsub(x3, x4))) / den;
-    const double u = -dsub(dmul(dsub(x1, x2), dsub(y1, y3)), dmul(dsub(y1, y2), dsub(x1, x3))) / den;
-    if (0 < t && t < 1 && u > 0) {
+    const double tn = dsub(dmul(dsub(x1, x3), dsub(y3, y4)), dmul(dsub(y1, y3), dsub(x3, x4)));
+    const double un = -dsub(dmul(dsub(x1, x2), dsub(y1, y3)), dmul(dsub(y1, y2), dsub(x1, x3)));
+    const bool dpos = den > 0;
+    const bool t_pos = dpos ? (tn > 0) : (tn < 0);
+    const bool t_lt1 = fabs(tn) < fabs(den);
+    const bool u_pos = dpos ? (un > 0) : (un < 0);
+    if (t_pos && t_lt1 && u_pos) {
+        const double t = tn / den;
         const double hx = dadd(x1, dmul(t, dsub(x2, x1))), hy = dadd(y1, dmul(t, dsub(y2, y1)));
         const double gx = dsub(ox, hx), gy = dsub(oy, hy);
         dist = sqrt(dadd(dmul(gx, gx), dmul(gy, gy)));
@@ -165,8 +194,13 @@ CE_HD_NOINLINE double exact_ray_distance(double ox, double oy, double dx, double
 
 // ---- action decode (lib/car_env.py:698-722) -------------------------------------------------
 CE_HD void decode_action(int a, int &thrust, int &turn) {
-    thrust = (a == 0 || a == 4 || a == 5) ? 1 : ((a == 1 || a == 6 || a == 7) ? -1 : 0);
-    turn = (a == 3 || a == 5 || a == 7) ? 1 : ((a == 2 || a == 4 || a == 6) ? -1 : 0);
+    // two bits per action: value + 1.  thrust: 0,4,5 -> +1; 1,6,7 -> -1.  turn: 3,5,7 -> +1 (right,
+    // rotation += 5); 2,4,6 -> -1 (left).  Anything else (8, or out of range) does nothing.
+    const unsigned kThrust = 2u | (0u << 2) | (1u << 4) | (1u << 6) | (2u << 8) | (2u << 10) | (0u << 12) | (0u << 14) | (1u << 16);
+    const unsigned kTurn = 1u | (1u << 2) | (0u << 4) | (2u << 6) | (0u << 8) | (2u << 10) | (0u << 12) | (2u << 14) | (1u << 16);
+    const unsigned sh = 2u * ((unsigned)a < 8u ? (unsigned)a : 8u);
+    thrust = (int)((kThrust >> sh) & 3u) - 1;
+    turn = (int)((kTurn >> sh) & 3u) - 1;
 }
 
 // ---- gate test with the pose left by the previous update (lib/car_env.py:725, 394-408) ------
@@ -273,6 +307,57 @@ CE_HD void wall_segment(WallAcc &w, const SegF &f, const SegD &g, double px, dou
     }
 }
 
+// Two consecutive segments j, j+1 of one polyline, packed: the lines l and l+3 (perpendicular) share
+// one FFMA2/FMUL2 each because q_l = x*s_l - y*c_l and q_{l+3} = x*c_l + y*s_l are the two components of
+// x*(s_l, c_l) + y*(-c_l, s_l).  Hits are selected arithmetically (r * mask, mask in {0,1} from FSET) so
+// that one 3-input max/min per ray folds both segments.  Every component is the same IEEE operation as
+// in wall_segment, so both paths give bit-identical results.
+struct WallAcc2 {
+    P2 S[3], C[3];          // S_l = (s_l, c_l), C_l = (-c_l, s_l)
+    float nphx, nphy;       // -float32(pos)
+    float Rp[6], Rm[6], gq[6], gu;
+    P2 QA[3];               // (q_l, q_{l+3}) of the previous endpoint
+};
+
+CE_HD void wall_point2(const WallAcc2 &w, float hx, float hy, P2 Q[3]) {
+    const float x = fadd(hx, w.nphx), y = fadd(hy, w.nphy);
+#pragma unroll
+    for (int l = 0; l < 3; ++l) Q[l] = pfma(p2(x, x), w.S[l], pmul(p2(y, y), w.C[l]));
+}
+
+CE_HD void wall_chain_start2(WallAcc2 &w, const SegF &f) {
+    wall_point2(w, f.ahx, f.ahy, w.QA);
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        w.gq[l] = fminf(w.gq[l], fabsf(w.QA[l].x));
+        w.gq[l + 3] = fminf(w.gq[l + 3], fabsf(w.QA[l].y));
+    }
+}
+
+CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1, const SegD &g1, double px,
+                     double py) {
+    P2 QB0[3], QB1[3];
+    wall_point2(w, f0.bhx, f0.bhy, QB0);
+    wall_point2(w, f1.bhx, f1.bhy, QB1);
+    const float un0 = (float)dfma(g0.ey, px, dfma(-g0.ex, py, g0.K));
+    const float un1 = (float)dfma(g1.ey, px, dfma(-g1.ex, py, g1.K));
+    const float inv0 = frcp(un0), inv1 = frcp(un1);
+    w.gu = fmin3(w.gu, fabsf(un0), fabsf(un1));
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const P2 R0 = pmul(pfma(p2(f0.ex, f0.ex), w.S[l], pmul(p2(f0.ey, f0.ey), w.C[l])), p2(inv0, inv0));
+        const P2 R1 = pmul(pfma(p2(f1.ex, f1.ex), w.S[l], pmul(p2(f1.ey, f1.ey), w.C[l])), p2(inv1, inv1));
+        const P2 W0 = pmul(w.QA[l], QB0[l]), W1 = pmul(QB0[l], QB1[l]);
+        const P2 H0 = pmul(R0, p2(neg_mask(W0.x), neg_mask(W0.y)));
+        const P2 H1 = pmul(R1, p2(neg_mask(W1.x), neg_mask(W1.y)));
+        w.Rp[l] = fmax3(w.Rp[l], H0.x, H1.x); w.Rm[l] = fmin3(w.Rm[l], H0.x, H1.x);
+        w.Rp[l + 3] = fmax3(w.Rp[l + 3], H0.y, H1.y); w.Rm[l + 3] = fmin3(w.Rm[l + 3], H0.y, H1.y);
+        w.gq[l] = fmin3(w.gq[l], fabsf(QB0[l].x), fabsf(QB1[l].x));
+        w.gq[l + 3] = fmin3(w.gq[l + 3], fabsf(QB0[l].y), fabsf(QB1[l].y));
+        w.QA[l] = QB1[l];
+    }
+}
+
 // dist[i] (pixels, float32) for ray i = heading + 30*i degrees; returns destroyed.
 // U = segments per loop iteration.  U > 1 requires (checked on the host, TrackParams::unroll) that
 // n_seg and every polyline start are multiples of U; the body is then U segments of straight-line
@@ -281,63 +366,92 @@ CE_HD void wall_segment(WallAcc &w, const SegF &f, const SegD &g, double px, dou
 template <int U>
 CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, float dist[kNumRays],
                       unsigned long long *stats) {
-    WallAcc w;
-    w.phx = (float)s.px; w.phy = (float)s.py;
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
-        const F2 d = T.trig32[wrap72(s.k + 6 * l)];
-        w.c[l] = d.x; w.sn[l] = d.y;
-    }
     const float R0 = 1.0e-3f;           // 1/1000: "no hit" (lib/car_env.py:198)
-#pragma unroll
-    for (int l = 0; l < 6; ++l) { w.Rp[l] = R0; w.Rm[l] = -R0; w.gq[l] = 1.0e30f; w.qa[l] = 0.0f; }
-    w.gu = 1.0e30f;
-
+    float Rp[6], Rm[6], gq[6], gu;
     if (U > 1) {
+        WallAcc2 w;
+        w.nphx = -(float)s.px; w.nphy = -(float)s.py;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const F2 d = T.trig32[wrap72(s.k + 6 * l)];
+            w.S[l] = p2(d.y, d.x); w.C[l] = p2(-d.x, d.y);
+            w.QA[l] = p2(0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int l = 0; l < 6; ++l) { w.Rp[l] = R0; w.Rm[l] = -R0; w.gq[l] = 1.0e30f; }
+        w.gu = 1.0e30f;
 #pragma unroll 1
         for (int j0 = 0; j0 < P.n_seg; j0 += U) {
-            if (P.segf[j0].chain_start) wall_chain_start(w, P.segf[j0]);
+            if (P.segf[j0].chain_start) wall_chain_start2(w, P.segf[j0]);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (u % 2 == 1) wall_segment<2>(w, P.segf[j0 + u], P.segd[j0 + u], s.px, s.py);
-                else if (u == U - 1) wall_segment<1>(w, P.segf[j0 + u], P.segd[j0 + u], s.px, s.py);
-                else wall_segment<0>(w, P.segf[j0 + u], P.segd[j0 + u], s.px, s.py);
-            }
+            for (int u = 0; u < U; u += 2)
+                wall_pair(w, P.segf[j0 + u], P.segd[j0 + u], P.segf[j0 + u + 1], P.segd[j0 + u + 1], s.px, s.py);
         }
+#pragma unroll
+        for (int l = 0; l < 6; ++l) { Rp[l] = w.Rp[l]; Rm[l] = w.Rm[l]; gq[l] = w.gq[l]; }
+        gu = w.gu;
     } else {
+        WallAcc w;
+        w.phx = (float)s.px; w.phy = (float)s.py;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const F2 d = T.trig32[wrap72(s.k + 6 * l)];
+            w.c[l] = d.x; w.sn[l] = d.y;
+        }
+#pragma unroll
+        for (int l = 0; l < 6; ++l) { w.Rp[l] = R0; w.Rm[l] = -R0; w.gq[l] = 1.0e30f; w.qa[l] = 0.0f; }
+        w.gu = 1.0e30f;
 #pragma unroll 1
         for (int j = 0; j < P.n_seg; ++j) {
             if (P.segf[j].chain_start) wall_chain_start(w, P.segf[j]);
             wall_segment<1>(w, P.segf[j], P.segd[j], s.px, s.py);
         }
+#pragma unroll
+        for (int l = 0; l < 6; ++l) { Rp[l] = w.Rp[l]; Rm[l] = w.Rm[l]; gq[l] = w.gq[l]; }
+        gu = w.gu;
     }
 
     // ---- decisions ---------------------------------------------------------------------------
+    // Common case (no guard tripped anywhere): branch-free.  One combined flag sends the warp to the
+    // careful per-line evaluation below (about 4e-4 of env-steps on the shipped tracks).
     const float r_tiny = frcp(P.tiny_d);
     const float r_coll = 0.1f;                    // d < 10  <=>  1/d > 0.1
     const float r_band = fmul(r_coll, P.coll_band);
-    const bool redo_all = w.gu < P.tiny_un;       // car (numerically) on a wall line: sign of u unknown
-    bool destroyed = false;
+    const float g_all = fmin3(fmin3(gq[0], gq[1], gq[2]), fmin3(gq[3], gq[4], gq[5]), 1.0e30f);
+    const float r_all = fmaxf(fmax3(fmax3(Rp[0], Rp[1], Rp[2]), fmax3(Rp[3], Rp[4], Rp[5]), 0.0f),
+                              -fmin3(fmin3(Rm[0], Rm[1], Rm[2]), fmin3(Rm[3], Rm[4], Rm[5]), 0.0f));
+    const float card_hi = fmax3(fmax3(Rp[0], Rp[3], -Rm[0]), -Rm[3], 0.0f);
+    const float band_lo = fmin3(fmin3(fabsf(fsub(Rp[0], r_coll)), fabsf(fsub(Rp[3], r_coll)), fabsf(fadd(Rm[0], r_coll))),
+                                fabsf(fadd(Rm[3], r_coll)), 1.0e30f);
+    bool destroyed = card_hi > r_coll;
 #pragma unroll
     for (int l = 0; l < 6; ++l) {
-        const bool cardinal = (l == 0 || l == 3);
-        bool redo = redo_all || (w.gq[l] < P.eps_q);
-        if (redo) stat_add(stats, kStatLine);
-        if (!redo && (w.Rp[l] > r_tiny || w.Rm[l] < -r_tiny)) { redo = true; stat_add(stats, kStatTiny); }
-        if (!redo && cardinal &&
-            (fabsf(fsub(w.Rp[l], r_coll)) < r_band || fabsf(fadd(w.Rm[l], r_coll)) < r_band)) {
-            redo = true; stat_add(stats, kStatBand);
-        }
-        if (!redo) {
-            dist[l] = w.Rp[l] > R0 ? frcp(w.Rp[l]) : 1000.0f;
-            dist[l + 6] = w.Rm[l] < -R0 ? -frcp(w.Rm[l]) : 1000.0f;
-            if (cardinal) destroyed = destroyed || (w.Rp[l] > r_coll) || (w.Rm[l] < -r_coll);
-        } else {
-            const D2 d0 = T.trig64[wrap72(s.k + 6 * l)], d1 = T.trig64[wrap72(s.k + 6 * l + 36)];
-            const double e0 = exact_ray_distance(s.px, s.py, d0.x, d0.y, T.walls64, P.n_seg);
-            const double e1 = exact_ray_distance(s.px, s.py, d1.x, d1.y, T.walls64, P.n_seg);
-            dist[l] = (float)e0; dist[l + 6] = (float)e1;
-            if (cardinal) destroyed = destroyed || (e0 < 10.0) || (e1 < 10.0);
+        dist[l] = Rp[l] > R0 ? frcp(Rp[l]) : 1000.0f;
+        dist[l + 6] = Rm[l] < -R0 ? -frcp(Rm[l]) : 1000.0f;
+    }
+    const bool careful = (gu < P.tiny_un) || (g_all < P.eps_q) || (r_all > r_tiny) || (band_lo < r_band);
+    if (careful) {
+        const bool redo_all = gu < P.tiny_un;     // car (numerically) on a wall line: sign of u unknown
+        destroyed = false;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+            const bool cardinal = (l == 0 || l == 3);
+            bool redo = redo_all || (gq[l] < P.eps_q);
+            if (redo) stat_add(stats, kStatLine);
+            if (!redo && (Rp[l] > r_tiny || Rm[l] < -r_tiny)) { redo = true; stat_add(stats, kStatTiny); }
+            if (!redo && cardinal &&
+                (fabsf(fsub(Rp[l], r_coll)) < r_band || fabsf(fadd(Rm[l], r_coll)) < r_band)) {
+                redo = true; stat_add(stats, kStatBand);
+            }
+            if (!redo) {
+                if (cardinal) destroyed = destroyed || (Rp[l] > r_coll) || (Rm[l] < -r_coll);
+            } else {
+                const D2 d0 = T.trig64[wrap72(s.k + 6 * l)], d1 = T.trig64[wrap72(s.k + 6 * l + 36)];
+                const double e0 = exact_ray_distance(s.px, s.py, d0.x, d0.y, T.walls64, P.n_seg);
+                const double e1 = exact_ray_distance(s.px, s.py, d1.x, d1.y, T.walls64, P.n_seg);
+                dist[l] = (float)e0; dist[l + 6] = (float)e1;
+                if (cardinal) destroyed = destroyed || (e0 < 10.0) || (e1 < 10.0);
+            }
         }
     }
     return destroyed;

@@ -111,9 +111,11 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
         s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
         s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
     }
+    int a_next = (int)actions[e];
     for (int t = 0; t < n_steps; ++t) {
         const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
-        const int a = (int)actions[idx];
+        const int a = a_next;
+        if (t + 1 < n_steps) a_next = (int)actions[idx + (size_t)n_envs];   // next step's action is in flight during this step
         StepResult o;
         env_step<U>(s, a, reward_scale, P, T, o, stats);
         if (obs_out) {

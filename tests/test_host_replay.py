@@ -59,3 +59,16 @@ def test_reward_scaling_is_float32_of_float64_product(tracks_dir):
     r64 = np.select([np.isclose(a["rew"], v) for v in (0.01, 1.0, 1.01, -3.0, -2.99, -2.0, -1.99)],
                     [0.01, 1.0, 0.01 + 1.0, -3.0, 0.01 - 3.0, 1.0 - 3.0, (0.01 + 1.0) - 3.0], 0.0)
     assert np.array_equal(b["rew"], (r64 * 0.1).astype(np.float32))
+
+
+def test_packed_and_scalar_wall_paths_are_bit_identical(tracks_dir):
+    """The FFMA2-packed pair path (U = 2, 4) and the scalar segment loop (U = 1) perform the same IEEE
+    operations per component: observations, rewards, flags and final state must be identical bits."""
+    rng = np.random.default_rng(17)
+    acts = rng.choice(9, size=(400, 256), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04]).astype(np.uint8)
+    for name in ("track", "big_track"):
+        path = os.path.join(tracks_dir, name + ".json")
+        a, b = emul_rollout(path, acts, unrolled=True), emul_rollout(path, acts, unrolled=False)
+        for k in ("obs", "rew", "term", "trunc", "info", "state_pv", "state_i"):
+            assert np.array_equal(a[k], b[k]), (name, k)
+        assert np.array_equal(a["stats"], b["stats"])

@@ -318,6 +318,27 @@ def run_ours(args):
         achieved_tflops = steps_per_launch * FLOP_PER_ENV_STEP / (launch_ms * 1e-3) / 1e12
         bytes_per_launch = steps_per_launch * BYTES_PER_ENV_STEP + n * 2 * STATE_BYTES
         achieved_gbs = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+        # secondary kernel: GAE reverse scan at BASELINE config 3 size [1024, 65536] (HBM-bound, 24 B/element)
+        Tg, Ng = 1024, 65536
+        gg = torch.Generator(device=dev).manual_seed(7)
+        g_rew = torch.rand((Tg, Ng), generator=gg, device=dev) * 1.4 - 0.3
+        g_val = torch.randn((Tg, Ng), generator=gg, device=dev)
+        g_term = (torch.rand((Tg, Ng), generator=gg, device=dev) < 0.004).float()
+        g_trunc = (torch.rand((Tg, Ng), generator=gg, device=dev) < 0.001).float()
+        g_lv, g_z = torch.randn(Ng, generator=gg, device=dev), torch.zeros(Ng, device=dev)
+        g_adv, g_ret = torch.empty_like(g_rew), torch.empty_like(g_rew)
+        for _ in range(3):
+            ppo_car_b200.gae_reverse_scan(g_rew, g_val, g_term, g_trunc, g_lv, g_z, g_z, adv_out=g_adv, ret_out=g_ret)
+        torch.cuda.synchronize()
+        ge = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
+        ge[0].record()
+        for i in range(10):
+            ppo_car_b200.gae_reverse_scan(g_rew, g_val, g_term, g_trunc, g_lv, g_z, g_z, adv_out=g_adv, ret_out=g_ret)
+            ge[i + 1].record()
+        torch.cuda.synchronize()
+        gae_ms = ge[0].elapsed_time(ge[-1]) / 10
+        gae_gbs = Tg * Ng * 24 / (gae_ms * 1e-3) / 1e9
+        del g_rew, g_val, g_term, g_trunc, g_adv, g_ret
         cpu = cpu_baseline(track) if not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
@@ -346,6 +367,9 @@ def run_ours(args):
             "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved_gbs / hbm_peak, "bytes_per_env_step": BYTES_PER_ENV_STEP,
                              "peak_source": hbm_src},
+            "gae": {"kernel": "k_gae", "shape": [Tg, Ng], "ms": gae_ms, "bound": "hbm", "achieved": gae_gbs,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": gae_gbs / hbm_peak, "bytes_per_element": 24,
+                    "note": "inputs + outputs 1.6 GB > L2; 10 back-to-back launches, CUDA events"},
             "slow_path": {k: v for k, v in slow.items()},
             "cpu_baseline": cpu,
         }

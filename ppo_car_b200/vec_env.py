@@ -133,8 +133,9 @@ class VecCarEnv:
     def _info_dict(self, info):
         if info is None:
             return {}
+        # views only (no per-step arithmetic on the host): "events" has bit 0 = gate hit, bit 1 = lap (+10)
         return {"gates_passed": info[..., 0], "time_passed": info[..., 1], "next_gate_index": info[..., 2],
-                "gate_hit": info[..., 3] & 1, "lap": (info[..., 3] >> 1) & 1}
+                "events": info[..., 3]}
 
     def step(self, actions):
         """One step of every environment with same-step autoreset (lib/car_env.py:693-760 +

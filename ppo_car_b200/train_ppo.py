@@ -1,0 +1,195 @@
+"""PPO loop harness on the GPU environment (BASELINE config 5).
+
+The caller of the hot path, restated from the reference's ``train.py:114-301`` so that the batched
+environment and the GAE kernel can be exercised exactly the way the reference uses them:
+
+  * same flags (``--n-envs --n-epochs --n-steps --batch-size --train-iters --gamma --gae-lambda
+    --clip-ratio --ent-coef --vf-coef --learning-rate --learning-rate-decay --max-grad-norm
+    --reward-scaling``, train.py:72-92) plus ``--track`` (the reference asks with a tkinter dialog);
+  * same network (actor 18-256-9, critic 18-256-1, orthogonal init with gains sqrt(2) / 0.01 / 1.0,
+    lib/model.py:6-26), Adam(lr, eps=1e-5) + StepLR(gamma = decay) (train.py:146-147);
+  * same update math: clipped surrogate, 0.5 * value MSE, entropy bonus, per-minibatch advantage
+    normalisation with max(std, 1e-5), grad-norm clip (train.py:233-261);
+  * same minibatch schedule: per train iteration only ``n_steps / batch_size`` minibatches are drawn
+    from the ``n_steps * n_envs`` samples (train.py:228 iterates over n_steps).  The reference shuffles
+    all indices on the host (O(T*N) per iteration); here the indices of the minibatches are sampled on
+    the device (uniform without the full permutation — at these sizes duplicates are negligible).
+
+What differs by design: nothing leaves the device during the rollout (the reference round-trips
+actions, observations, rewards and flags through the host every step, train.py:185-192), GAE is one
+kernel launch, and with more than one process (torchrun) every rank owns an env shard and gradients
+are averaged with one NCCL all-reduce per minibatch step (12,298 floats).
+
+    python -m ppo_car_b200.train_ppo --track big_track --n-envs 24 --n-epochs 200
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import time
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import Buffer, VecCarEnv, builtin_track
+from .shard import allreduce_rollout_stats, shard_range
+
+
+def _ortho(layer: nn.Linear, gain: float) -> nn.Linear:
+    nn.init.orthogonal_(layer.weight, gain)
+    nn.init.zeros_(layer.bias)
+    return layer
+
+
+class ActorCritic(nn.Module):
+    """Two independent 2-layer MLPs (lib/model.py:10-26)."""
+
+    def __init__(self, obs_dim: int, n_actions: int, hidden: int = 256):
+        super().__init__()
+        g = math.sqrt(2.0)
+        self.actor = nn.Sequential(_ortho(nn.Linear(obs_dim, hidden), g), nn.ReLU(),
+                                   _ortho(nn.Linear(hidden, n_actions), 0.01))
+        self.critic = nn.Sequential(_ortho(nn.Linear(obs_dim, hidden), g), nn.ReLU(),
+                                    _ortho(nn.Linear(hidden, 1), 1.0))
+
+    def value(self, obs):
+        return self.critic(obs)
+
+    def act(self, obs, action=None):
+        logp_all = torch.log_softmax(self.actor(obs), dim=-1)
+        if action is None:
+            action = torch.multinomial(logp_all.exp(), 1).squeeze(-1)
+        logp = logp_all.gather(-1, action.long().unsqueeze(-1)).squeeze(-1)
+        entropy = -(logp_all.exp() * logp_all).sum(-1)
+        return action, logp, entropy, self.critic(obs)
+
+
+def parse_args(argv=None):
+    p = argparse.ArgumentParser()
+    p.add_argument("--run-name", default="b200")
+    p.add_argument("--track", default="big_track", help="track name shipped with the package or a JSON path")
+    p.add_argument("--n-envs", type=int, default=16, help="total environments over all ranks")
+    p.add_argument("--n-epochs", type=int, default=200)
+    p.add_argument("--n-steps", type=int, default=1024)
+    p.add_argument("--batch-size", type=int, default=512)
+    p.add_argument("--train-iters", type=int, default=40)
+    p.add_argument("--gamma", type=float, default=0.99)
+    p.add_argument("--gae-lambda", type=float, default=0.95)
+    p.add_argument("--clip-ratio", type=float, default=0.2)
+    p.add_argument("--ent-coef", type=float, default=0.001)
+    p.add_argument("--vf-coef", type=float, default=0.5)
+    p.add_argument("--learning-rate", type=float, default=3e-4)
+    p.add_argument("--learning-rate-decay", type=float, default=0.99)
+    p.add_argument("--max-grad-norm", type=float, default=1.0)
+    p.add_argument("--reward-scaling", type=float, default=0.1)
+    p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--log-json", default=None, help="append one JSON line per epoch to this file")
+    return p.parse_args(argv)
+
+
+def train(args) -> list[dict]:
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(args.seed)                       # same initial weights on every rank
+    track = args.track if os.path.exists(args.track) else builtin_track(args.track)
+    lo, hi = shard_range(args.n_envs, world, rank)
+    n = hi - lo
+    T = args.n_steps
+
+    envs = VecCarEnv(n, track, device=dev, reward_scaling=args.reward_scaling, float_flags=True, with_info=False)
+    obs_dim = envs.single_observation_space.shape
+    agent = ActorCritic(obs_dim[0], envs.single_action_space.n).to(dev)
+    opt = torch.optim.Adam(agent.parameters(), lr=args.learning_rate, eps=1e-5)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=args.learning_rate_decay)
+    params = [p for p in agent.parameters()]
+    buf = Buffer(obs_dim, T, n, dev, args.gamma, args.gae_lambda)
+    torch.manual_seed(args.seed * 1000 + rank + 1)     # different sampling noise per shard
+
+    next_obs = envs.reset()[0].clone()
+    next_term = torch.zeros(n, device=dev)
+    next_trunc = torch.zeros(n, device=dev)
+    history, global_step, t_start = [], 0, time.time()
+    n_mb = max(1, T // args.batch_size)
+
+    for epoch in range(1, args.n_epochs + 1):
+        # ---- rollout (train.py:173-195): everything stays on the device
+        with torch.no_grad():
+            for _ in range(T):
+                obs, term, trunc = next_obs, next_term, next_trunc
+                act, logp, _, val = agent.act(obs)
+                o, rew, te, tr, _ = envs.step(act)
+                buf.store(obs, act, rew, val.view(-1), term, trunc, logp)
+                next_obs, next_term, next_trunc = o.clone(), te.clone(), tr.clone()
+            global_step += T * args.n_envs
+            adv, ret = buf.calculate_advantages(agent.value(next_obs).reshape(1, -1), next_term.reshape(1, -1),
+                                                next_trunc.reshape(1, -1))
+        rew_sum, steps, episodes = allreduce_rollout_stats(buf.rew_buf.sum(), torch.tensor(float(T * n), device=dev),
+                                                           buf.term_buf.sum() + buf.trunc_buf.sum())
+        obs_b, act_b, val_b, logp_b = buf.get()
+        obs_f, act_f, logp_f = obs_b.view(-1, *obs_dim), act_b.view(-1), logp_b.view(-1)
+        adv_f, ret_f = adv.view(-1), ret.view(-1)
+
+        # ---- update (train.py:223-261)
+        sums = torch.zeros(4, device=dev)
+        for _ in range(args.train_iters):
+            idx_all = torch.randint(0, T * n, (n_mb, args.batch_size), device=dev)
+            for m in range(n_mb):
+                idx = idx_all[m]
+                _, new_logp, ent, new_val = agent.act(obs_f[idx], act_f[idx])
+                ratio = torch.exp(new_logp - logp_f[idx])
+                a = adv_f[idx]
+                a = (a - a.mean()) / torch.clamp(a.std(), min=1e-5)
+                pol = torch.max(-a * ratio, -a * torch.clamp(ratio, 1 - args.clip_ratio, 1 + args.clip_ratio)).mean()
+                vl = 0.5 * ((new_val.view(-1) - ret_f[idx]) ** 2).mean()
+                e = ent.mean()
+                loss = pol + args.vf_coef * vl - args.ent_coef * e
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                if world > 1:                                   # average the 12,298 gradients over the shards
+                    flat = torch.cat([p.grad.reshape(-1) for p in params])
+                    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                    flat /= world
+                    off = 0
+                    for p in params:
+                        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                        off += p.numel()
+                nn.utils.clip_grad_norm_(params, args.max_grad_norm)
+                opt.step()
+                sums += torch.stack([pol.detach(), vl.detach(), e.detach(), loss.detach()])
+        sched.step()
+
+        s = (sums / args.train_iters).tolist()
+        rec = {"epoch": epoch, "global_step": global_step, "avg_reward": rew_sum / steps / args.reward_scaling,
+               "episodes": episodes, "policy_loss": s[0], "value_loss": s[1], "entropy": s[2], "total_loss": s[3],
+               "lr": opt.param_groups[0]["lr"], "sps": global_step / (time.time() - t_start),
+               "wall_s": time.time() - t_start}
+        history.append(rec)
+        if rank == 0:
+            print(f"Epoch {epoch} done in {rec['wall_s']:.2f}s. Avg reward: {rec['avg_reward']:.4f}. "
+                  f"SPS {rec['sps']:.0f}  entropy {rec['entropy']:.3f}", flush=True)
+            if args.log_json:
+                import json
+
+                with open(args.log_json, "a") as fh:
+                    fh.write(json.dumps(rec) + "\n")
+    envs.close()
+    return history
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    train(args)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,7 +62,10 @@ struct DeviceGuard {
     }
 };
 
-constexpr int kBlock = 128;
+#ifndef CARENV_BLOCK
+#define CARENV_BLOCK 128
+#endif
+constexpr int kBlock = CARENV_BLOCK;
 
 template <typename FlagT> __device__ __forceinline__ FlagT make_flag(int v);
 template <> __device__ __forceinline__ uint8_t make_flag<uint8_t>(int v) { return (uint8_t)v; }

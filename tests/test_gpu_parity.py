@@ -185,3 +185,27 @@ def test_buffer_store_rows_from_env_step(tracks_dir):
     ra, rr = gae_port(buf.rew_buf.cpu().numpy(), buf.val_buf.cpu().numpy(), buf.term_buf.cpu().numpy(),
                       buf.trunc_buf.cpu().numpy(), np.zeros(n, np.float32), term.cpu().numpy(), trunc.cpu().numpy())
     assert np.array_equal(adv.cpu().numpy(), ra) and np.array_equal(ret.cpu().numpy(), rr)
+
+
+def test_host_step_pipeline_large_batch(tracks_dir):
+    """The numpy-in / numpy-out path cuts large batches into sub-ranges on side streams; results must equal
+    the single-launch device path, also when device-side and host-side calls are interleaved."""
+    path = os.path.join(tracks_dir, "big_track.json")
+    n = 200_003                                        # >= 131072 -> 4 ranges, ragged sizes
+    env_h, env_d = ppo_car_b200.VecCarEnv(n, path), ppo_car_b200.VecCarEnv(n, path)
+    env_h.reset()
+    env_d.reset()
+    rng = np.random.default_rng(8)
+    for t in range(40):
+        a = rng.integers(0, 9, size=n)
+        od, rd, ted, trd, idd = env_d.step(torch.from_numpy(a).cuda())
+        if t % 5 == 4:                                 # interleave a device-side call on the default stream
+            oh, rh, teh, trh, ih = env_h.step(torch.from_numpy(a).cuda())
+            oh, rh, teh, trh = oh.cpu().numpy(), rh.cpu().numpy(), teh.cpu().numpy(), trh.cpu().numpy()
+            ih = {k: v.cpu().numpy() for k, v in ih.items()}
+        else:
+            oh, rh, teh, trh, ih = env_h.step(a)
+        assert np.array_equal(oh, od.cpu().numpy()) and np.array_equal(rh, rd.cpu().numpy())
+        assert np.array_equal(teh, ted.cpu().numpy()) and np.array_equal(trh, trd.cpu().numpy())
+        assert np.array_equal(ih["gates_passed"], idd["gates_passed"].cpu().numpy())
+    assert torch.equal(env_h.pos, env_d.pos) and torch.equal(env_h.ints, env_d.ints)

@@ -151,10 +151,25 @@ k_reset(const __grid_constant__ TrackParams P, int n_envs, double2 *__restrict__
     }
 }
 
-// GAE(lambda), lib/buffer.py:51-63.  The recurrence is serial in t but the loads are not: the
-// loop is unrolled so that kGaeUnroll timesteps of loads are in flight per thread.
+// GAE(lambda), lib/buffer.py:51-63.  The recurrence is serial in t but the loads are not: timesteps are
+// processed in batches of kGaeUnroll with the NEXT batch's 4 * kGaeUnroll loads issued before the
+// current batch is consumed (register double buffering), so every thread keeps loads in flight while
+// it walks the dependent chain.  Streaming loads/stores: every byte is touched once.
 constexpr int kGaeUnroll = 8;
-__global__ void __launch_bounds__(256)
+
+struct GaeBatch { float r[kGaeUnroll], v[kGaeUnroll], te[kGaeUnroll], tr[kGaeUnroll]; };
+
+__device__ __forceinline__ void gae_load(GaeBatch &b, const float *__restrict__ rew, const float *__restrict__ val,
+                                         const float *__restrict__ term, const float *__restrict__ trunc, int t,
+                                         size_t N, size_t e) {
+#pragma unroll
+    for (int i = 0; i < kGaeUnroll; ++i) {
+        const size_t k = (size_t)(t - i) * N + e;
+        b.r[i] = __ldcs(rew + k); b.v[i] = __ldcs(val + k); b.te[i] = __ldcs(term + k); b.tr[i] = __ldcs(trunc + k);
+    }
+}
+
+__global__ void __launch_bounds__(128)
 k_gae(const float *__restrict__ rew, const float *__restrict__ val, const float *__restrict__ term,
       const float *__restrict__ trunc, const float *__restrict__ last_val, const float *__restrict__ last_term,
       const float *__restrict__ last_trunc, float *__restrict__ adv, float *__restrict__ ret, int T, int N, float g,
@@ -166,24 +181,23 @@ k_gae(const float *__restrict__ rew, const float *__restrict__ val, const float 
     float um = __fadd_rn(1.0f, -last_trunc[e]);
     float a = 0.0f;
     int t = T - 1;
+    GaeBatch cur, nxt;
+    if (t >= kGaeUnroll - 1) gae_load(cur, rew, val, term, trunc, t, (size_t)N, (size_t)e);
     for (; t >= kGaeUnroll - 1; t -= kGaeUnroll) {
-        float r[kGaeUnroll], v[kGaeUnroll], te[kGaeUnroll], tr[kGaeUnroll];
+        const bool more = (t - kGaeUnroll) >= kGaeUnroll - 1;
+        if (more) gae_load(nxt, rew, val, term, trunc, t - kGaeUnroll, (size_t)N, (size_t)e);
 #pragma unroll
         for (int i = 0; i < kGaeUnroll; ++i) {
             const size_t k = (size_t)(t - i) * (size_t)N + (size_t)e;
-            r[i] = __ldcs(rew + k); v[i] = __ldcs(val + k); te[i] = __ldcs(term + k); tr[i] = __ldcs(trunc + k);
-        }
-#pragma unroll
-        for (int i = 0; i < kGaeUnroll; ++i) {
-            const size_t k = (size_t)(t - i) * (size_t)N + (size_t)e;
-            const float delta = __fadd_rn(__fadd_rn(r[i], __fmul_rn(__fmul_rn(g, nv), tm)), -v[i]);
+            const float delta = __fadd_rn(__fadd_rn(cur.r[i], __fmul_rn(__fmul_rn(g, nv), tm)), -cur.v[i]);
             a = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(gl, tm), um), a));
             __stcs(adv + k, a);
-            __stcs(ret + k, __fadd_rn(a, v[i]));
-            nv = v[i];
-            tm = __fadd_rn(1.0f, -te[i]);
-            um = __fadd_rn(1.0f, -tr[i]);
+            __stcs(ret + k, __fadd_rn(a, cur.v[i]));
+            nv = cur.v[i];
+            tm = __fadd_rn(1.0f, -cur.te[i]);
+            um = __fadd_rn(1.0f, -cur.tr[i]);
         }
+        if (more) cur = nxt;
     }
     for (; t >= 0; --t) {
         const size_t k = (size_t)t * (size_t)N + (size_t)e;
@@ -404,8 +418,8 @@ int gae_reverse_scan(const float *rew, const float *val, const float *term, cons
         return fail(CARENV_E_INVAL, "null pointer");
     const float g = (float)gamma;
     const float gl = (float)(gamma * gae_lambda);   // evaluated in double first (lib/buffer.py:61)
-    const int grid = (N + 255) / 256;
-    k_gae<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(rew, val, term, trunc, last_val, last_term, last_trunc,
+    const int grid = (N + 127) / 128;
+    k_gae<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(rew, val, term, trunc, last_val, last_term, last_trunc,
                                                               adv, ret, T, N, g, gl);
     CU(cudaGetLastError());
     return 0;

@@ -86,6 +86,9 @@ def parse_args(argv=None):
     p.add_argument("--reward-scaling", type=float, default=0.1)
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--log-json", default=None, help="append one JSON line per epoch to this file")
+    p.add_argument("--cuda-graph", action="store_true",
+                   help="capture the whole n_steps rollout (policy forward, sampling, env step, buffer rows) in one "
+                        "CUDA graph and replay it every epoch: removes the per-step launch overhead at small n_envs")
     return p.parse_args(argv)
 
 
@@ -113,21 +116,50 @@ def train(args) -> list[dict]:
     buf = Buffer(obs_dim, T, n, dev, args.gamma, args.gae_lambda)
     torch.manual_seed(args.seed * 1000 + rank + 1)     # different sampling noise per shard
 
+    # the rollout state lives in three static tensors so that the loop below can be captured in a graph
     next_obs = envs.reset()[0].clone()
     next_term = torch.zeros(n, device=dev)
     next_trunc = torch.zeros(n, device=dev)
     history, global_step, t_start = [], 0, time.time()
     n_mb = max(1, T // args.batch_size)
 
-    for epoch in range(1, args.n_epochs + 1):
-        # ---- rollout (train.py:173-195): everything stays on the device
+    def rollout():
+        """train.py:173-195 with everything on the device: row t of the buffer gets (obs_t, a_t, r_t, V(obs_t),
+        term_t, trunc_t, logp_t); the env's outputs become the next step's inputs."""
+        buf.ptr = 0
+        for _ in range(T):
+            act, logp, _, val = agent.act(next_obs)
+            buf.store(next_obs, act, 0.0, val.view(-1), next_term, next_trunc, logp)
+            o, rew, te, tr, _ = envs.step(act)
+            buf.rew_buf[buf.ptr - 1].copy_(rew)
+            next_obs.copy_(o)
+            next_term.copy_(te)
+            next_trunc.copy_(tr)
+
+    graph = None
+    if args.cuda_graph:
         with torch.no_grad():
-            for _ in range(T):
-                obs, term, trunc = next_obs, next_term, next_trunc
-                act, logp, _, val = agent.act(obs)
-                o, rew, te, tr, _ = envs.step(act)
-                buf.store(obs, act, rew, val.view(-1), term, trunc, logp)
-                next_obs, next_term, next_trunc = o.clone(), te.clone(), tr.clone()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                  # warm-up outside capture (lazy inits, autotuning)
+                rollout()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            next_obs.copy_(envs.reset()[0])                # discard the warm-up rollout
+            next_term.zero_()
+            next_trunc.zero_()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                rollout()
+
+    for epoch in range(1, args.n_epochs + 1):
+        # ---- rollout
+        with torch.no_grad():
+            if graph is not None:
+                graph.replay()
+                buf.ptr = T
+            else:
+                rollout()
             global_step += T * args.n_envs
             adv, ret = buf.calculate_advantages(agent.value(next_obs).reshape(1, -1), next_term.reshape(1, -1),
                                                 next_trunc.reshape(1, -1))

@@ -209,3 +209,27 @@ def test_host_step_pipeline_large_batch(tracks_dir):
         assert np.array_equal(teh, ted.cpu().numpy()) and np.array_equal(trh, trd.cpu().numpy())
         assert np.array_equal(ih["gates_passed"], idd["gates_passed"].cpu().numpy())
     assert torch.equal(env_h.pos, env_d.pos) and torch.equal(env_h.ints, env_d.ints)
+
+
+@pytest.mark.parametrize("n_outer,n_inner", [(7, 5), (10, 6), (16, 12)])
+def test_other_segment_counts_on_gpu(tmp_path, n_outer, n_inner):
+    """Synthetic tracks: odd polyline sizes run the generic loop, even ones the 2-/4-segment unrolled kernels;
+    forcing the generic kernel must give identical bits."""
+    from tests.synth_tracks import ring_track
+
+    path = ring_track(str(tmp_path / "ring.json"), n_outer, n_inner)
+    rng = np.random.default_rng(n_outer)
+    acts = rng.choice(9, size=(400, 1024), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04]).astype(np.uint8)
+    ora = COracleVecEnv(1024, path, scan_all_gates=True)
+    ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    env = ppo_car_b200.VecCarEnv(1024, path)
+    env.reset()
+    out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
+    assert_trajectory_matches(_gpu_traj(out), ref, what=f"ring {n_outer}+{n_inner}")
+    gen = ppo_car_b200.VecCarEnv(1024, path)
+    gen.set_option("force_generic", 1)
+    gen.reset()
+    out2 = gen.rollout(torch.from_numpy(acts).cuda(), store_info=True)
+    assert torch.equal(out["obs"], out2["obs"]) and torch.equal(out["reward"], out2["reward"])
+    assert torch.equal(out["terminated"], out2["terminated"]) and torch.equal(env.pos, gen.pos)

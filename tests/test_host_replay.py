@@ -72,3 +72,21 @@ def test_packed_and_scalar_wall_paths_are_bit_identical(tracks_dir):
         for k in ("obs", "rew", "term", "trunc", "info", "state_pv", "state_i"):
             assert np.array_equal(a[k], b[k]), (name, k)
         assert np.array_equal(a["stats"], b["stats"])
+
+
+@pytest.mark.parametrize("n_outer,n_inner", [(7, 5), (10, 6), (16, 12), (31, 29)])
+def test_other_segment_counts_match_oracle(tmp_path, n_outer, n_inner):
+    """Tracks with other polyline sizes pick other loop unrollings (1, 2, 4): all must follow the oracle."""
+    from tests.synth_tracks import ring_track
+
+    path = ring_track(str(tmp_path / "ring.json"), n_outer, n_inner)
+    rng = np.random.default_rng(n_outer)
+    acts = rng.choice(9, size=(400, 512), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04]).astype(np.uint8)
+    ora = COracleVecEnv(512, path, scan_all_gates=True)
+    ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    e = emul_rollout(path, acts)
+    got = dict(obs=e["obs"], rew=e["rew"], term=e["term"], trunc=e["trunc"], gates_passed=e["info"][..., 0],
+               time_passed=e["info"][..., 1], next_gate_index=e["info"][..., 2])
+    assert_trajectory_matches(got, ref, what=f"ring {n_outer}+{n_inner}")
+    assert ref["term"].sum() > 50 and ref["gates_passed"].max() > 0

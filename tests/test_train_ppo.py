@@ -38,3 +38,12 @@ def test_short_training_run_improves_reward():
     hist = train(args)
     assert len(hist) == 12 and all(math.isfinite(h["total_loss"]) for h in hist)
     assert hist[-1]["avg_reward"] > hist[0]["avg_reward"] + 0.03       # random policy is about 0.0
+
+
+@pytest.mark.gpu
+def test_cuda_graph_rollout_trains():
+    args = parse_args(["--track", "track", "--n-envs", "32", "--n-epochs", "10", "--n-steps", "256", "--cuda-graph"])
+    hist = train(args)
+    assert all(math.isfinite(h["total_loss"]) for h in hist)
+    assert hist[-1]["avg_reward"] > hist[0]["avg_reward"] + 0.02
+    assert hist[0]["episodes"] > 0

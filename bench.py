@@ -112,7 +112,7 @@ def cpu_baseline(track_path, target_seconds=12.0):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(threading.Thread):
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period, [], set(), None
         self._stop_evt = threading.Event()
@@ -339,6 +339,12 @@ def run_ours(args):
         gae_ms = ge[0].elapsed_time(ge[-1]) / 10
         gae_gbs = Tg * Ng * 24 / (gae_ms * 1e-3) / 1e9
         del g_rew, g_val, g_term, g_trunc, g_adv, g_ret
+        traffic = None
+        try:   # measured DRAM bytes per env-step of the same kernel from the committed ncu capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            traffic = tr["dram_bytes_per_env_step"] * steps_per_launch
+        except Exception:
+            pass
         cpu = cpu_baseline(track) if not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
@@ -358,14 +364,17 @@ def run_ours(args):
                     "steps": e_steps},
             "gpu_launches": args.steps * launches,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_nominal, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / fp32_nominal, "traffic": None,
+                         "frac": achieved_tflops / fp32_nominal, "traffic": traffic,
+                         "traffic_note": "DRAM bytes per launch (ncu dram__bytes_read+write per env-step x env-steps per "
+                                         "launch, profiles/r1_traffic.json); algorithmic bytes per launch = "
+                                         f"{bytes_per_launch}",
                          "kernel": "k_rollout<uint8,uint8>", "launch_ms": launch_ms,
                          "flop_per_env_step": FLOP_PER_ENV_STEP,
                          "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no "
                                         "FP32 entry)",
                          "ffma_probe_tflops": ffma_tflops, "frac_of_ffma_probe": achieved_tflops / ffma_tflops},
             "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved_gbs / hbm_peak, "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                             "frac": achieved_gbs / hbm_peak, "traffic": traffic, "bytes_per_env_step": BYTES_PER_ENV_STEP,
                              "peak_source": hbm_src},
             "gae": {"kernel": "k_gae", "shape": [Tg, Ng], "ms": gae_ms, "bound": "hbm", "achieved": gae_gbs,
                     "peak": hbm_peak, "unit": "GB/s", "frac": gae_gbs / hbm_peak, "bytes_per_element": 24,

@@ -47,6 +47,7 @@ struct Handle {
     unsigned long long *d_stats;
     size_t smem_bytes;
     int force_generic;        // test hook: run the generic (not unrolled) kernel
+    int max_unroll;           // tuning hook: cap the segment-loop unrolling (0 = no cap)
 };
 
 struct DeviceGuard {
@@ -253,7 +254,8 @@ template <typename ActT, typename FlagT>
 int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints, const void *actions,
                    double reward_scale, float *obs_out, float *reward_out, void *term_out, void *trunc_out,
                    int32_t *info_out, cudaStream_t stream) {
-    const int U = h->force_generic ? 1 : h->host.P.unroll;
+    int U = h->force_generic ? 1 : h->host.P.unroll;
+    if (h->max_unroll > 0 && U > h->max_unroll) U = h->max_unroll;
 #define ARGS h, n_envs, n_steps, pos, vel, ints, actions, reward_scale, obs_out, reward_out, term_out, trunc_out, info_out, stream
     if (U == 4) return launch_rollout_t<ActT, FlagT, 4>(ARGS);
     if (U == 2) return launch_rollout_t<ActT, FlagT, 2>(ARGS);
@@ -307,7 +309,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -395,6 +397,7 @@ int carenv_set_option(void *handle, const char *name, int value) {
     Handle *h = static_cast<Handle *>(handle);
     if (!h || !name) return fail(CARENV_E_INVAL, "null argument");
     if (std::string(name) == "force_generic") { h->force_generic = value ? 1 : 0; return 0; }
+    if (std::string(name) == "max_unroll") { h->max_unroll = value; return 0; }
     return fail(CARENV_E_INVAL, std::string("unknown option ") + name);
 }
 

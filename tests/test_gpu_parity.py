@@ -233,3 +233,24 @@ def test_other_segment_counts_on_gpu(tmp_path, n_outer, n_inner):
     out2 = gen.rollout(torch.from_numpy(acts).cuda(), store_info=True)
     assert torch.equal(out["obs"], out2["obs"]) and torch.equal(out["reward"], out2["reward"])
     assert torch.equal(out["terminated"], out2["terminated"]) and torch.equal(env.pos, gen.pos)
+
+
+def test_config3_size_integer_traces_bit_exact(tracks_dir):
+    """BASELINE config 3 width (65,536 envs) x 512 steps = 33.5 M env-steps (about 125 k episodes) against the
+    float64 oracle: every terminated / truncated / gates_passed / time_passed / next_gate_index element equal."""
+    path = os.path.join(tracks_dir, "big_track.json")
+    n, T = 65536, 512
+    g = torch.Generator(device="cuda").manual_seed(42)
+    acts = torch.randint(0, 9, (T, n), generator=g, device="cuda", dtype=torch.uint8)
+    env = ppo_car_b200.VecCarEnv(n, path)
+    env.reset()
+    out = env.rollout(acts, store_obs=False, store_info=True)
+    ora = COracleVecEnv(n, path, scan_all_gates=False)
+    ora.reset()
+    ref = ora.rollout(acts.cpu().numpy(), want=("rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    assert np.array_equal(out["terminated"].cpu().numpy(), ref["term"])
+    assert np.array_equal(out["truncated"].cpu().numpy(), ref["trunc"])
+    for k in ("gates_passed", "time_passed", "next_gate_index"):
+        assert np.array_equal(out["info"][k].cpu().numpy(), ref[k]), k
+    assert np.array_equal(out["reward"].cpu().numpy(), ref["rew"].astype(np.float32))
+    assert ref["term"].sum() > 100_000

@@ -53,9 +53,9 @@ struct D2 { double x, y; };
 // One wall segment A->B in float32 (endpoints rounded from float64; they only feed sign tests).
 struct SegF {
     float ahx, ahy, bhx, bhy;
-    float ex, ey;          // B - A rounded from float64
+    float ex;              // B - A rounded from float64
+    float ney, ey;         // (-ey, ey) adjacent: one packed operand of the den computation
     int chain_start;       // 1: A is not the previous segment's B
-    int pad;
 };
 struct SegD { double K, ex, ey; };   // K = cross(e, A):  cross(e, A - pos) = K - (ex*py - ey*px)
 
@@ -313,16 +313,18 @@ CE_HD void wall_segment(WallAcc &w, const SegF &f, const SegD &g, double px, dou
 // that one 3-input max/min per ray folds both segments.  Every component is the same IEEE operation as
 // in wall_segment, so both paths give bit-identical results.
 struct WallAcc2 {
-    P2 S[3], C[3];          // S_l = (s_l, c_l), C_l = (-c_l, s_l)
-    float nphx, nphy;       // -float32(pos)
+    P2 S[3];                // S_l = (s_l, c_l); its half-swap (c_l, s_l) is a free operand modifier
+    float phx, phy;         // float32(pos)
     float Rp[6], Rm[6], gq[6], gu;
     P2 QA[3];               // (q_l, q_{l+3}) of the previous endpoint
 };
 
+// (q_l, q_{l+3}) = x*(s_l, c_l) + (-y, y)*(c_l, s_l): only S_l is kept in registers (keeping the rotated
+// pair (-c_l, s_l) as well made the compiler rebuild it in every loop iteration).
 CE_HD void wall_point2(const WallAcc2 &w, float hx, float hy, P2 Q[3]) {
-    const float x = fadd(hx, w.nphx), y = fadd(hy, w.nphy);
+    const float x = fsub(hx, w.phx), y = fsub(hy, w.phy), yn = fsub(w.phy, hy);   // yn == -y exactly
 #pragma unroll
-    for (int l = 0; l < 3; ++l) Q[l] = pfma(p2(x, x), w.S[l], pmul(p2(y, y), w.C[l]));
+    for (int l = 0; l < 3; ++l) Q[l] = pfma(p2(x, x), w.S[l], pmul(p2(yn, y), p2(w.S[l].y, w.S[l].x)));
 }
 
 CE_HD void wall_chain_start2(WallAcc2 &w, const SegF &f) {
@@ -345,8 +347,9 @@ CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1
     w.gu = fmin3(w.gu, fabsf(un0), fabsf(un1));
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
-        const P2 R0 = pmul(pfma(p2(f0.ex, f0.ex), w.S[l], pmul(p2(f0.ey, f0.ey), w.C[l])), p2(inv0, inv0));
-        const P2 R1 = pmul(pfma(p2(f1.ex, f1.ex), w.S[l], pmul(p2(f1.ey, f1.ey), w.C[l])), p2(inv1, inv1));
+        const P2 SW = p2(w.S[l].y, w.S[l].x);
+        const P2 R0 = pmul(pfma(p2(f0.ex, f0.ex), w.S[l], pmul(p2(f0.ney, f0.ey), SW)), p2(inv0, inv0));
+        const P2 R1 = pmul(pfma(p2(f1.ex, f1.ex), w.S[l], pmul(p2(f1.ney, f1.ey), SW)), p2(inv1, inv1));
         const P2 W0 = pmul(w.QA[l], QB0[l]), W1 = pmul(QB0[l], QB1[l]);
         const P2 H0 = pmul(R0, p2(neg_mask(W0.x), neg_mask(W0.y)));
         const P2 H1 = pmul(R1, p2(neg_mask(W1.x), neg_mask(W1.y)));
@@ -370,11 +373,11 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
     float Rp[6], Rm[6], gq[6], gu;
     if (U > 1) {
         WallAcc2 w;
-        w.nphx = -(float)s.px; w.nphy = -(float)s.py;
+        w.phx = (float)s.px; w.phy = (float)s.py;
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             const F2 d = T.trig32[wrap72(s.k + 6 * l)];
-            w.S[l] = p2(d.y, d.x); w.C[l] = p2(-d.x, d.y);
+            w.S[l] = p2(d.y, d.x);
             w.QA[l] = p2(0.0f, 0.0f);
         }
 #pragma unroll

@@ -48,7 +48,7 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
         SegF &f = P.segf[j];
         f.ahx = (float)ax; f.ahy = (float)ay; f.bhx = (float)bx; f.bhy = (float)by;
         const double ex = bx - ax, ey = by - ay;
-        f.ex = (float)ex; f.ey = (float)ey;
+        f.ex = (float)ex; f.ey = (float)ey; f.ney = -f.ey;
         f.chain_start = (j == 0 || walls[4 * j - 2] != ax || walls[4 * j - 1] != ay) ? 1 : 0;
         P.segd[j] = SegD{fma(ex, ay, -(ey * ax)), ex, ey};
         const double len = hypot(ex, ey);

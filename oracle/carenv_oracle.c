@@ -33,7 +33,7 @@
 
 #define N_RAYS 12
 #define OBS_DIM 18
-#define MAX_GATES 1024
+#define MAX_GATES 4096
 
 typedef struct {
     double px, py, vx, vy, ax, ay, rot;

@@ -254,3 +254,47 @@ def test_config3_size_integer_traces_bit_exact(tracks_dir):
         assert np.array_equal(out["info"][k].cpu().numpy(), ref[k]), k
     assert np.array_equal(out["reward"].cpu().numpy(), ref["rew"].astype(np.float32))
     assert ref["term"].sum() > 100_000
+
+
+def test_limits_many_gates_and_max_segments(tmp_path):
+    """128 wall segments (the parameter-space limit) and 1,500 gates (gate table > 48 KB of shared memory,
+    which needs the opt-in dynamic shared memory attribute); one more segment is rejected with an error."""
+    from tests.synth_tracks import ring_track
+
+    path = ring_track(str(tmp_path / "big_ring.json"), 64, 64, n_gates=1500, wobble=0.03)
+    rng = np.random.default_rng(1)
+    acts = rng.choice(9, size=(300, 512), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04]).astype(np.uint8)
+    ora = COracleVecEnv(512, path, scan_all_gates=False)
+    ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    env = ppo_car_b200.VecCarEnv(512, path)
+    env.reset()
+    out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
+    assert_trajectory_matches(_gpu_traj(out), ref, what="64+64 segments, 1500 gates")
+    assert ref["gates_passed"].max() > 20
+    too_big = ring_track(str(tmp_path / "too_big.json"), 65, 64)
+    with pytest.raises(ppo_car_b200.CarEnvError, match="segments"):
+        ppo_car_b200.VecCarEnv(8, too_big)
+
+
+def test_api_errors_and_out_of_range_actions(tracks_dir):
+    path = os.path.join(tracks_dir, "track.json")
+    env = ppo_car_b200.VecCarEnv(16, path)
+    with pytest.raises(ppo_car_b200.CarEnvError):
+        env.step(np.zeros(16, np.int64))                      # step before reset
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step(np.zeros(15, np.int64))
+    with pytest.raises(FileNotFoundError):
+        env.reset(options={"track_path": os.path.join(tracks_dir, "missing.json")})
+    # an action outside 0..8 falls through the reference's if/elif chain: same as "do nothing" (8)
+    a = ppo_car_b200.VecCarEnv(16, path)
+    b = ppo_car_b200.VecCarEnv(16, path)
+    a.reset()
+    b.reset()
+    for _ in range(30):
+        oa, ra, *_ = a.step(torch.full((16,), 8, device="cuda"))
+        ob, rb, *_ = b.step(torch.full((16,), 11, device="cuda"))
+        assert torch.equal(oa, ob) and torch.equal(ra, rb)
+    env.close()
+    env.close()                                               # idempotent

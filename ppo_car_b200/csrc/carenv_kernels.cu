@@ -156,7 +156,10 @@ k_reset(const __grid_constant__ TrackParams P, int n_envs, double2 *__restrict__
 // processed in batches of kGaeUnroll with the NEXT batch's 4 * kGaeUnroll loads issued before the
 // current batch is consumed (register double buffering), so every thread keeps loads in flight while
 // it walks the dependent chain.  Streaming loads/stores: every byte is touched once.
-constexpr int kGaeUnroll = 8;
+#ifndef CARENV_GAE_UNROLL
+#define CARENV_GAE_UNROLL 8
+#endif
+constexpr int kGaeUnroll = CARENV_GAE_UNROLL;
 
 struct GaeBatch { float r[kGaeUnroll], v[kGaeUnroll], te[kGaeUnroll], tr[kGaeUnroll]; };
 

@@ -110,6 +110,22 @@ int gae_reverse_scan(const float *rew, const float *val, const float *term, cons
                      const float *last_val, const float *last_term, const float *last_trunc, float *adv, float *ret,
                      int T, int N, double gamma, double gae_lambda, void *stream);
 
+/* Fused rollout (the loop of train.py:173-195 in one launch): for n_steps steps, per environment:
+ * actor/critic forward (lib/model.py:10-40, float32), categorical sample by inverse CDF on a Philox4x32-10
+ * uniform keyed by (seed; env_offset + env, step0 + t), Buffer row writes (lib/buffer.py:22-34: obs, action
+ * as float32, reward, value, the flags that came WITH the observation, logprob), CarEnv.step with autoreset.
+ *   packed_weights  device float[carenv_policy_weights_floats()] in the layout of ppo_car_b200/policy.py
+ *   cur_obs [n][18], cur_term [n], cur_trunc [n]   in: observation/flags the rollout starts from; out: those it ends with
+ *   *_buf           [n_steps][n_envs](,18) float32 Buffer tensors
+ *   last_val [n] or NULL  critic value of the final observation (bootstrap for GAE, train.py:200)
+ *   u_dbg [n_steps][n_envs] or NULL  the uniforms that were used (tests) */
+int carenv_policy_weights_floats(void);
+int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs, int n_steps, int env_offset,
+                          unsigned long long seed, unsigned long long step0, double *pos, double *vel, int32_t *ints,
+                          float *cur_obs, float *cur_term, float *cur_trunc, double reward_scale, float *obs_buf,
+                          float *act_buf, float *rew_buf, float *val_buf, float *term_buf, float *trunc_buf,
+                          float *logp_buf, float *last_val, float *u_dbg, void *stream);
+
 /* Measurement helper (no reference counterpart): an FFMA-only kernel, blocks x 256 threads x
  * iters x 64 FFMA, used by bench.py to measure the FP32-pipe peak the step kernel is compared with. */
 int carenv_bench_ffma(int blocks, int iters, float *scratch, void *stream);

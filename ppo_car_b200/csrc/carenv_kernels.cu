@@ -18,6 +18,7 @@
 
 #include "../../include/carenv_b200.h"
 #include "carenv_tables.h"
+#include "policy_core.cuh"
 
 using namespace carenv;
 
@@ -135,6 +136,87 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
     pos[e] = make_double2(s.px, s.py);
     vel[e] = make_double2(s.vx, s.vy);
     ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+}
+
+// Fused rollout: actor/critic forward, categorical sampling, CarEnv.step and the Buffer
+// row writes of train.py:173-195 for n_steps steps in ONE launch.  One thread per environment; the packed
+// policy weights (53 KB) and the per-thread-indexed track tables live in shared memory.
+template <int U>
+__global__ void __launch_bounds__(kBlock, 3)
+k_policy_rollout(const __grid_constant__ TrackParams P, const Tables G, const float *__restrict__ weights,
+                 int n_envs, int n_steps, int env_offset, unsigned long long seed, unsigned long long step0,
+                 double2 *__restrict__ pos, double2 *__restrict__ vel, int4 *__restrict__ ints,
+                 float *__restrict__ cur_obs, float *__restrict__ cur_term, float *__restrict__ cur_trunc,
+                 double reward_scale, float *__restrict__ obs_buf, float *__restrict__ act_buf,
+                 float *__restrict__ rew_buf, float *__restrict__ val_buf, float *__restrict__ term_buf,
+                 float *__restrict__ trunc_buf, float *__restrict__ logp_buf, float *__restrict__ last_val,
+                 float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *sw = reinterpret_cast<float *>(smem + table_bytes);
+    for (int i = threadIdx.x; i < kPolicyFloats / 4; i += blockDim.x)
+        reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(weights)[i];
+    const Tables T = stage_tables(G, P.n_gates, smem);      // ends with __syncthreads()
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+
+    EnvState s;
+    {
+        const double2 p = pos[e], v = vel[e];
+        const int4 q = ints[e];
+        s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
+        s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
+    }
+    float obs[kObsDim];
+    {
+        const float2 *src = reinterpret_cast<const float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+        for (int i = 0; i < kObsDim / 2; ++i) { const float2 v = src[i]; obs[2 * i] = v.x; obs[2 * i + 1] = v.y; }
+    }
+    float tc = cur_term[e], uc = cur_trunc[e];
+    const uint32_t gid = (uint32_t)(env_offset + e);
+    PolicyOut po;
+    for (int t = 0; t < n_steps; ++t) {
+        const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+        policy_forward(obs, sw, po);
+        const unsigned long long gs = step0 + (unsigned long long)t;
+        const uint32_t bits = philox_uniform_bits((uint32_t)seed, (uint32_t)(seed >> 32), gid, (uint32_t)gs,
+                                                  (uint32_t)(gs >> 32), 0x43415245u);
+        const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
+        float logp, us;
+        const int a = sample_action(po, u, logp, us);
+        {
+            float2 *dst = reinterpret_cast<float2 *>(obs_buf + idx * kObsDim);
+#pragma unroll
+            for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+        }
+        act_buf[idx] = (float)a;
+        val_buf[idx] = po.value;
+        logp_buf[idx] = logp;
+        term_buf[idx] = tc;
+        trunc_buf[idx] = uc;
+        if (u_dbg) u_dbg[idx] = u;
+        StepResult o;
+        env_step<U>(s, a, reward_scale, P, T, o, stats);
+        rew_buf[idx] = o.reward;
+#pragma unroll
+        for (int i = 0; i < kObsDim; ++i) obs[i] = o.obs[i];
+        tc = o.terminated ? 1.0f : 0.0f;
+        uc = o.truncated ? 1.0f : 0.0f;
+    }
+    pos[e] = make_double2(s.px, s.py);
+    vel[e] = make_double2(s.vx, s.vy);
+    ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+    {
+        float2 *dst = reinterpret_cast<float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+        for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+    }
+    cur_term[e] = tc;
+    cur_trunc[e] = uc;
+    if (last_val) {                                          // bootstrap value of the state after the rollout
+        policy_forward(obs, sw, po);
+        last_val[e] = po.value;
+    }
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -394,6 +476,42 @@ int carenv_rollout(void *handle, int n_envs, int n_steps, double *pos, double *v
                    void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream) {
     return dispatch_rollout(handle, n_envs, n_steps, pos, vel, ints, actions, action_dtype, reward_scale, obs_out,
                             reward_out, term_out, trunc_out, flag_dtype, info_out, stream);
+}
+
+int carenv_policy_weights_floats(void) { return kPolicyFloats; }
+
+int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs, int n_steps, int env_offset,
+                          unsigned long long seed, unsigned long long step0, double *pos, double *vel, int32_t *ints,
+                          float *cur_obs, float *cur_term, float *cur_trunc, double reward_scale, float *obs_buf,
+                          float *act_buf, float *rew_buf, float *val_buf, float *term_buf, float *trunc_buf,
+                          float *logp_buf, float *last_val, float *u_dbg, void *stream) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(CARENV_E_INVAL, "null handle");
+    if (n_envs < 0 || n_steps < 0) return fail(CARENV_E_INVAL, "negative n_envs / n_steps");
+    if (n_envs == 0) return 0;
+    if (!packed_weights || !pos || !vel || !ints || !cur_obs || !cur_term || !cur_trunc || !obs_buf || !act_buf ||
+        !rew_buf || !val_buf || !term_buf || !trunc_buf || !logp_buf)
+        return fail(CARENV_E_INVAL, "null pointer");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    const int table_bytes = (int)((h->smem_bytes + 15) / 16 * 16);
+    const size_t smem = (size_t)table_bytes + sizeof(float) * kPolicyFloats;
+    const int grid = (n_envs + kBlock - 1) / kBlock;
+    int U = h->force_generic ? 1 : h->host.P.unroll;
+    if (h->max_unroll > 0 && U > h->max_unroll) U = h->max_unroll;
+    auto launch = [&](auto kern) -> int {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kBlock, smem, static_cast<cudaStream_t>(stream)>>>(
+            h->host.P, h->dev, packed_weights, n_envs, n_steps, env_offset, seed, step0,
+            reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints), cur_obs,
+            cur_term, cur_trunc, reward_scale, obs_buf, act_buf, rew_buf, val_buf, term_buf, trunc_buf, logp_buf,
+            last_val, u_dbg, h->d_stats, table_bytes);
+        CU(cudaGetLastError());
+        return 0;
+    };
+    if (U == 4) return launch(k_policy_rollout<4>);
+    if (U == 2) return launch(k_policy_rollout<2>);
+    return launch(k_policy_rollout<1>);
 }
 
 int carenv_set_option(void *handle, const char *name, int value) {

@@ -1,0 +1,71 @@
+"""Fused rollout: policy forward + sampling + CarEnv.step + Buffer rows in one kernel launch.
+
+Host side of ``carenv_policy_rollout`` (include/carenv_b200.h).  The network is the reference's
+(lib/model.py:10-26): actor 18-256-9 and critic 18-256-1, two ``nn.Sequential(Linear, ReLU, Linear)``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+HIDDEN, OBS, ACTIONS = 256, 18, 9
+
+
+def pack_policy_weights(actor, critic, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Lay the four Linear layers out the way policy_core.cuh reads them: per pair of hidden units
+    (j, j+1) an actor block [18 x (W1[j,k], W1[j+1,k]) | b1 pair, pad | 5 x (W2[2q,j], W2[2q+1,j],
+    W2[2q,j+1], W2[2q+1,j+1])] of 60 floats and a critic block [18 pairs | b1 pair, pad | (W2c[j],
+    W2c[j+1]), pad] of 44 floats, then b2[0..9] (b2[9] = 0), b2c, pad.  Cheap enough to redo after
+    every optimiser step (12,298 parameters)."""
+    w1a, b1a, w2a, b2a = actor[0].weight, actor[0].bias, actor[2].weight, actor[2].bias
+    w1c, b1c, w2c, b2c = critic[0].weight, critic[0].bias, critic[2].weight, critic[2].bias
+    if tuple(w1a.shape) != (HIDDEN, OBS) or tuple(w2a.shape) != (ACTIONS, HIDDEN) or tuple(w2c.shape) != (1, HIDDEN):
+        raise ValueError("fused rollout supports the reference network only: 18-256-9 actor, 18-256-1 critic")
+    dev, P = w1a.device, HIDDEN // 2
+    with torch.no_grad():
+        z2 = torch.zeros((P, 2), device=dev)
+        w2pad = torch.cat([w2a, torch.zeros((1, HIDDEN), device=dev)])                 # [10, 256]
+        blk_a = torch.cat([w1a.view(P, 2, OBS).permute(0, 2, 1).reshape(P, 36), b1a.view(P, 2), z2,
+                           w2pad.view(5, 2, P, 2).permute(2, 0, 3, 1).reshape(P, 20)], dim=1)          # [128, 60]
+        blk_c = torch.cat([w1c.view(P, 2, OBS).permute(0, 2, 1).reshape(P, 36), b1c.view(P, 2), z2,
+                           w2c.view(P, 2), z2], dim=1)                                                  # [128, 44]
+        tail = torch.cat([b2a, torch.zeros(1, device=dev), b2c, torch.zeros(1, device=dev)])            # 12
+        packed = torch.cat([torch.cat([blk_a, blk_c], dim=1).reshape(-1), tail]).float().contiguous()
+    if packed.numel() != _lib.lib().carenv_policy_weights_floats():
+        raise _lib.CarEnvError("packed policy size does not match the library")
+    if out is not None:
+        out.copy_(packed)
+        return out
+    return packed
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def fused_rollout(env, packed: torch.Tensor, buf, cur_obs: torch.Tensor, cur_term: torch.Tensor,
+                  cur_trunc: torch.Tensor, seed: int, step0: int, env_offset: int = 0,
+                  last_val: torch.Tensor | None = None, u_dbg: torch.Tensor | None = None) -> None:
+    """Fill every row of ``buf`` (ppo_car_b200.Buffer) with one launch and leave the rollout state in
+    ``cur_obs / cur_term / cur_trunc`` (in place).  ``step0`` is the global step index of row 0 (it
+    selects the random stream together with ``seed`` and ``env_offset + env``)."""
+    n, T = env.num_envs, buf.capacity
+    for name, t, shape in (("cur_obs", cur_obs, (n, OBS)), ("cur_term", cur_term, (n,)), ("cur_trunc", cur_trunc, (n,)),
+                           ("last_val", last_val, (n,)), ("u_dbg", u_dbg, (T, n))):
+        if t is not None and (tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_contiguous()
+                              or t.device != env.device):
+            raise ValueError(f"{name} must be a contiguous float32 tensor of shape {shape} on {env.device}")
+    if tuple(buf.obs_buf.shape) != (T, n, OBS):
+        raise ValueError("buffer shape does not match the environment")
+    L = _lib.lib()
+    with torch.cuda.device(env.device):
+        rc = L.carenv_policy_rollout(env._handle, _p(packed), n, T, int(env_offset), int(seed) & (2 ** 64 - 1),
+                                     int(step0), _p(env.pos), _p(env.vel), _p(env.ints), _p(cur_obs), _p(cur_term),
+                                     _p(cur_trunc), float(env.reward_scaling), _p(buf.obs_buf), _p(buf.act_buf),
+                                     _p(buf.rew_buf), _p(buf.val_buf), _p(buf.term_buf), _p(buf.trunc_buf),
+                                     _p(buf.logprob_buf), _p(last_val), _p(u_dbg), env._stream())
+    _lib.check(rc, "carenv_policy_rollout")
+    buf.ptr = T

@@ -86,6 +86,9 @@ def parse_args(argv=None):
     p.add_argument("--reward-scaling", type=float, default=0.1)
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--log-json", default=None, help="append one JSON line per epoch to this file")
+    p.add_argument("--fused-rollout", action="store_true",
+                   help="run the whole rollout (policy forward, sampling, env step, buffer rows) in ONE kernel launch "
+                        "per epoch (carenv_policy_rollout); needs the reference network shape")
     p.add_argument("--cuda-graph", action="store_true",
                    help="capture the whole n_steps rollout (policy forward, sampling, env step, buffer rows) in one "
                         "CUDA graph and replay it every epoch: removes the per-step launch overhead at small n_envs")
@@ -136,8 +139,15 @@ def train(args) -> list[dict]:
             next_term.copy_(te)
             next_trunc.copy_(tr)
 
+    packed = last_val = None
+    if args.fused_rollout:
+        from .policy import fused_rollout, pack_policy_weights
+
+        packed = pack_policy_weights(agent.actor, agent.critic)
+        last_val = torch.empty(n, device=dev)
+
     graph = None
-    if args.cuda_graph:
+    if args.cuda_graph and not args.fused_rollout:
         with torch.no_grad():
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -155,14 +165,20 @@ def train(args) -> list[dict]:
     for epoch in range(1, args.n_epochs + 1):
         # ---- rollout
         with torch.no_grad():
-            if graph is not None:
-                graph.replay()
-                buf.ptr = T
+            if packed is not None:
+                pack_policy_weights(agent.actor, agent.critic, out=packed)
+                fused_rollout(envs, packed, buf, next_obs, next_term, next_trunc, seed=args.seed,
+                              step0=(epoch - 1) * T, env_offset=lo, last_val=last_val)
+                boot = last_val.reshape(1, -1)
             else:
-                rollout()
+                if graph is not None:
+                    graph.replay()
+                    buf.ptr = T
+                else:
+                    rollout()
+                boot = agent.value(next_obs).reshape(1, -1)
             global_step += T * args.n_envs
-            adv, ret = buf.calculate_advantages(agent.value(next_obs).reshape(1, -1), next_term.reshape(1, -1),
-                                                next_trunc.reshape(1, -1))
+            adv, ret = buf.calculate_advantages(boot, next_term.reshape(1, -1), next_trunc.reshape(1, -1))
         rew_sum, steps, episodes = allreduce_rollout_stats(buf.rew_buf.sum(), torch.tensor(float(T * n), device=dev),
                                                            buf.term_buf.sum() + buf.trunc_buf.sum())
         obs_b, act_b, val_b, logp_b = buf.get()

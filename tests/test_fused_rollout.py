@@ -1,0 +1,92 @@
+"""Fused rollout kernel against a plain PyTorch float32 evaluation of the same network and
+against the non-fused environment kernel."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ppo_car_b200
+from ppo_car_b200.train_ppo import ActorCritic, parse_args, train
+
+
+def test_pack_layout_matches_header_constants():
+    torch.manual_seed(0)
+    net = ActorCritic(18, 9)
+    if not os.path.exists(ppo_car_b200._lib.LIB_PATH):
+        pytest.skip("library not built")
+    packed = ppo_car_b200.pack_policy_weights(net.actor, net.critic)
+    assert packed.numel() == 128 * 104 + 12
+    blk = packed[:128 * 104].view(128, 104)
+    j = 7
+    assert blk[j, 0] == net.actor[0].weight[2 * j, 0] and blk[j, 1] == net.actor[0].weight[2 * j + 1, 0]
+    assert blk[j, 36] == net.actor[0].bias[2 * j] and blk[j, 40] == net.actor[2].weight[0, 2 * j]
+    assert blk[j, 41] == net.actor[2].weight[1, 2 * j] and blk[j, 42] == net.actor[2].weight[0, 2 * j + 1]
+    assert blk[j, 60 + 36] == net.critic[0].bias[2 * j] and blk[j, 60 + 40] == net.critic[2].weight[0, 2 * j]
+    assert packed[128 * 104 + 10] == net.critic[2].bias[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [24, 1000])
+def test_fused_rollout_matches_torch_policy_and_env_kernel(tracks_dir, n):
+    dev = torch.device("cuda")
+    path = os.path.join(tracks_dir, "big_track.json")
+    T = 300
+    torch.manual_seed(3)
+    net = ActorCritic(18, 9).to(dev)
+    with torch.no_grad():                                   # make the policy non-uniform so sampling matters
+        net.actor[2].weight.mul_(40.0)
+        net.actor[2].bias.copy_(torch.linspace(-1, 1, 9))
+    env = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1, float_flags=True)
+    buf = ppo_car_b200.Buffer((18,), T, n, dev)
+    cur_obs = env.reset()[0].clone()
+    cur_term, cur_trunc = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    last_val, u = torch.empty(n, device=dev), torch.empty((T, n), device=dev)
+    packed = ppo_car_b200.pack_policy_weights(net.actor, net.critic)
+    ppo_car_b200.fused_rollout(env, packed, buf, cur_obs, cur_term, cur_trunc, seed=11, step0=5, last_val=last_val, u_dbg=u)
+    torch.cuda.synchronize()
+    assert buf.ptr == T
+
+    # (1) network outputs: float32 torch evaluation of the same weights on the stored observations
+    with torch.no_grad():
+        logits = net.actor(buf.obs_buf.view(-1, 18)).view(T, n, 9)
+        val = net.critic(buf.obs_buf.view(-1, 18)).view(T, n)
+        logp_all = torch.log_softmax(logits, -1)
+    act = buf.act_buf.long()
+    assert torch.allclose(buf.val_buf, val, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(buf.logprob_buf, logp_all.gather(-1, act.unsqueeze(-1)).squeeze(-1), rtol=1e-5, atol=1e-5)
+    with torch.no_grad():
+        assert torch.allclose(last_val, net.critic(cur_obs).view(-1), rtol=1e-5, atol=1e-5)
+    # (2) sampling: the action is the inverse CDF of the recorded uniform (ties within 1e-5 of a boundary excused)
+    cdf = torch.softmax(logits, -1).cumsum(-1)
+    expect = (u.unsqueeze(-1) >= cdf).sum(-1).clamp(max=8)
+    near = ((cdf - u.unsqueeze(-1)).abs() < 1e-5).any(-1)
+    assert ((expect == act) | near).all() and near.float().mean() < 1e-3
+    assert 0.0 <= float(u.min()) and float(u.max()) < 1.0 and abs(float(u.mean()) - 0.5) < 0.01
+    assert len(torch.unique(act)) == 9
+    # (3) environment: replaying the sampled actions through the plain rollout kernel gives the same rows
+    env2 = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1, float_flags=True)
+    obs0 = env2.reset()[0].clone()
+    out = env2.rollout(act.to(torch.uint8))
+    assert torch.equal(buf.obs_buf[0], obs0) and torch.equal(buf.obs_buf[1:], out["obs"][:-1])
+    assert torch.equal(buf.rew_buf, out["reward"])
+    assert torch.equal(buf.term_buf[1:], out["terminated"][:-1]) and torch.equal(buf.trunc_buf[1:], out["truncated"][:-1])
+    assert torch.equal(cur_obs, out["obs"][-1]) and torch.equal(cur_term, out["terminated"][-1])
+    assert torch.equal(env.pos, env2.pos) and torch.equal(env.ints, env2.ints)
+    # (4) the random stream depends on (seed, global env id, global step) only: shard invariance
+    half = n // 2
+    env3 = ppo_car_b200.VecCarEnv(n - half, path, reward_scaling=0.1, float_flags=True)
+    buf3 = ppo_car_b200.Buffer((18,), T, n - half, dev)
+    o3 = env3.reset()[0].clone()
+    z = torch.zeros(n - half, device=dev)
+    ppo_car_b200.fused_rollout(env3, packed, buf3, o3, z.clone(), z.clone(), seed=11, step0=5, env_offset=half)
+    assert torch.equal(buf3.act_buf, buf.act_buf[:, half:]) and torch.equal(buf3.rew_buf, buf.rew_buf[:, half:])
+
+
+@pytest.mark.gpu
+def test_training_with_fused_rollout_improves_reward():
+    args = parse_args(["--track", "big_track", "--n-envs", "64", "--n-epochs", "12", "--n-steps", "256", "--fused-rollout"])
+    hist = train(args)
+    assert all(math.isfinite(h["total_loss"]) for h in hist)
+    assert hist[-1]["avg_reward"] > hist[0]["avg_reward"] + 0.03

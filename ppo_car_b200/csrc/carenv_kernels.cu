@@ -141,8 +141,15 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
 // Fused rollout: actor/critic forward, categorical sampling, CarEnv.step and the Buffer
 // row writes of train.py:173-195 for n_steps steps in ONE launch.  One thread per environment; the packed
 // policy weights (53 KB) and the per-thread-indexed track tables live in shared memory.
+#ifndef CARENV_POLICY_BLOCK
+#define CARENV_POLICY_BLOCK 128
+#endif
+#ifndef CARENV_POLICY_MIN_BLOCKS
+#define CARENV_POLICY_MIN_BLOCKS 3
+#endif
+constexpr int kPolicyBlock = CARENV_POLICY_BLOCK;
 template <int U>
-__global__ void __launch_bounds__(kBlock, 3)
+__global__ void __launch_bounds__(kPolicyBlock, CARENV_POLICY_MIN_BLOCKS)
 k_policy_rollout(const __grid_constant__ TrackParams P, const Tables G, const float *__restrict__ weights,
                  int n_envs, int n_steps, int env_offset, unsigned long long seed, unsigned long long step0,
                  double2 *__restrict__ pos, double2 *__restrict__ vel, int4 *__restrict__ ints,
@@ -496,12 +503,12 @@ int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs,
     if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
     const int table_bytes = (int)((h->smem_bytes + 15) / 16 * 16);
     const size_t smem = (size_t)table_bytes + sizeof(float) * kPolicyFloats;
-    const int grid = (n_envs + kBlock - 1) / kBlock;
+    const int grid = (n_envs + kPolicyBlock - 1) / kPolicyBlock;
     int U = h->force_generic ? 1 : h->host.P.unroll;
     if (h->max_unroll > 0 && U > h->max_unroll) U = h->max_unroll;
     auto launch = [&](auto kern) -> int {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kBlock, smem, static_cast<cudaStream_t>(stream)>>>(
+        kern<<<grid, kPolicyBlock, smem, static_cast<cudaStream_t>(stream)>>>(
             h->host.P, h->dev, packed_weights, n_envs, n_steps, env_offset, seed, step0,
             reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints), cur_obs,
             cur_term, cur_trunc, reward_scale, obs_buf, act_buf, rew_buf, val_buf, term_buf, trunc_buf, logp_buf,

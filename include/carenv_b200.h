@@ -126,6 +126,21 @@ int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs,
                           float *act_buf, float *rew_buf, float *val_buf, float *term_buf, float *trunc_buf,
                           float *logp_buf, float *last_val, float *u_dbg, void *stream);
 
+/* Tensor-core variant of the fused rollout: the two 18->256 layers run as tcgen05.mma kind::tf32 (3xTF32
+ * split, float32-level accuracy) with accumulators in tensor memory; same arguments and results (to float32
+ * rounding of the network outputs) as carenv_policy_rollout.  packed_weights: device
+ * float[carenv_policy_weights_floats_tc()] from ppo_car_b200.policy.pack_policy_weights_tc. */
+int carenv_policy_weights_floats_tc(void);
+int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_envs, int n_steps, int env_offset,
+                             unsigned long long seed, unsigned long long step0, double *pos, double *vel,
+                             int32_t *ints, float *cur_obs, float *cur_term, float *cur_trunc, double reward_scale,
+                             float *obs_buf, float *act_buf, float *rew_buf, float *val_buf, float *term_buf,
+                             float *trunc_buf, float *logp_buf, float *last_val, float *u_dbg, void *stream);
+
+/* Test hook for the tensor-core building blocks (csrc/tc_mlp.cuh): D[128][256] = A[128][24] * B[256][24]^T,
+ * tcgen05.mma kind::tf32 with the accumulator in tensor memory; device pointers, row-major float32. */
+int carenv_tc_gemm_test(const float *A, const float *B, float *D, void *stream);
+
 /* Measurement helper (no reference counterpart): an FFMA-only kernel, blocks x 256 threads x
  * iters x 64 FFMA, used by bench.py to measure the FP32-pipe peak the step kernel is compared with. */
 int carenv_bench_ffma(int blocks, int iters, float *scratch, void *stream);

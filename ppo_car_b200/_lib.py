@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("CARENV_LIB") or os.path.join(_PKG, "libcarenv_b200.so")   # override: kernel experiments
 SOURCES = [os.path.join(_PKG, "csrc", f)
-           for f in ("carenv_kernels.cu", "carenv_core.cuh", "carenv_tables.h", "policy_core.cuh")]
+           for f in ("carenv_kernels.cu", "carenv_core.cuh", "carenv_tables.h", "policy_core.cuh", "tc_mlp.cuh")]
 HEADER = os.path.join(ROOT, "include", "carenv_b200.h")
 
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
@@ -69,11 +69,15 @@ def lib():
     L.carenv_set_option.argtypes = [vp, C.c_char_p, i32]
     L.gae_reverse_scan.argtypes = [vp] * 9 + [i32, i32, f64, f64, vp]
     L.carenv_bench_ffma.argtypes = [i32, i32, vp, vp]
+    L.carenv_tc_gemm_test.argtypes = [vp, vp, vp, vp]
+    L.carenv_tc_gemm_test.restype = i32
     L.carenv_policy_weights_floats.restype = i32
     L.carenv_policy_rollout.argtypes = [vp, vp, i32, i32, i32, C.c_ulonglong, C.c_ulonglong, vp, vp, vp, vp, vp, vp,
                                         f64] + [vp] * 10
+    L.carenv_policy_weights_floats_tc.restype = i32
+    L.carenv_policy_rollout_tc.argtypes = L.carenv_policy_rollout.argtypes
     for name in ("carenv_create", "carenv_destroy", "carenv_reset_obs", "carenv_reset", "carenv_step",
-                 "carenv_rollout", "carenv_stats", "gae_reverse_scan", "carenv_bench_ffma", "carenv_set_option", "carenv_policy_rollout"):
+                 "carenv_rollout", "carenv_stats", "gae_reverse_scan", "carenv_bench_ffma", "carenv_set_option", "carenv_policy_rollout", "carenv_policy_rollout_tc"):
         getattr(L, name).restype = i32
     if L.carenv_abi_version() != 1:
         raise CarEnvError("libcarenv_b200.so ABI version mismatch; rebuild")

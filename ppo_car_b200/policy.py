@@ -42,13 +42,57 @@ def pack_policy_weights(actor, critic, out: torch.Tensor | None = None) -> torch
     return packed
 
 
+def _tf32(x: torch.Tensor) -> torch.Tensor:
+    """Round float32 to TF32 (10 explicit mantissa bits), to nearest with ties away from zero (cvt.rna)."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def pack_policy_weights_tc(actor, critic, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Weights for the tensor-core kernel: per net the first layer [256 x 24] (18 inputs, the bias in column
+    18, zero padding) as TF32 hi and lo parts in the K-major no-swizzle UMMA shared-memory layout
+    (csrc/tc_mlp.cuh: float index (j/8)*192 + (k/4)*32 + (j%8)*4 + k%4), then the actor's second layer as
+    [j][5] pairs (W2[2q][j], W2[2q+1][j]), the critic's second layer w2c[j], b2[0..9] (b2[9] = 0), b2c."""
+    w1a, b1a, w2a, b2a = actor[0].weight, actor[0].bias, actor[2].weight, actor[2].bias
+    w1c, b1c, w2c, b2c = critic[0].weight, critic[0].bias, critic[2].weight, critic[2].bias
+    if tuple(w1a.shape) != (HIDDEN, OBS) or tuple(w2a.shape) != (ACTIONS, HIDDEN) or tuple(w2c.shape) != (1, HIDDEN):
+        raise ValueError("fused rollout supports the reference network only: 18-256-9 actor, 18-256-1 critic")
+    dev = w1a.device
+    with torch.no_grad():
+        j = torch.arange(HIDDEN, device=dev).view(-1, 1)
+        k = torch.arange(24, device=dev).view(1, -1)
+        index = ((j // 8) * 192 + (k // 4) * 32 + (j % 8) * 4 + (k % 4)).reshape(-1)
+
+        def operand(w1, b1):
+            ext = torch.zeros((HIDDEN, 24), device=dev)
+            ext[:, :OBS] = w1
+            ext[:, OBS] = b1
+            hi = _tf32(ext)
+            lo = _tf32(ext - hi)
+            o_hi, o_lo = torch.empty(HIDDEN * 24, device=dev), torch.empty(HIDDEN * 24, device=dev)
+            o_hi[index] = hi.reshape(-1)
+            o_lo[index] = lo.reshape(-1)
+            return o_hi, o_lo
+
+        w2pad = torch.cat([w2a, torch.zeros((1, HIDDEN), device=dev)])                 # [10, 256]
+        packed = torch.cat([*operand(w1a, b1a), *operand(w1c, b1c), w2pad.t().reshape(-1), w2c.reshape(-1), b2a,
+                            torch.zeros(1, device=dev), b2c, torch.zeros(1, device=dev)]).float().contiguous()
+    if packed.numel() != _lib.lib().carenv_policy_weights_floats_tc():
+        raise _lib.CarEnvError("packed policy size does not match the library")
+    if out is not None:
+        out.copy_(packed)
+        return out
+    return packed
+
+
 def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
 def fused_rollout(env, packed: torch.Tensor, buf, cur_obs: torch.Tensor, cur_term: torch.Tensor,
                   cur_trunc: torch.Tensor, seed: int, step0: int, env_offset: int = 0,
-                  last_val: torch.Tensor | None = None, u_dbg: torch.Tensor | None = None) -> None:
+                  last_val: torch.Tensor | None = None, u_dbg: torch.Tensor | None = None,
+                  tensor_cores: bool | None = None) -> None:
     """Fill every row of ``buf`` (ppo_car_b200.Buffer) with one launch and leave the rollout state in
     ``cur_obs / cur_term / cur_trunc`` (in place).  ``step0`` is the global step index of row 0 (it
     selects the random stream together with ``seed`` and ``env_offset + env``)."""
@@ -61,11 +105,13 @@ def fused_rollout(env, packed: torch.Tensor, buf, cur_obs: torch.Tensor, cur_ter
     if tuple(buf.obs_buf.shape) != (T, n, OBS):
         raise ValueError("buffer shape does not match the environment")
     L = _lib.lib()
+    if tensor_cores is None:                                # the two packings have different sizes
+        tensor_cores = packed.numel() == L.carenv_policy_weights_floats_tc()
+    fn = L.carenv_policy_rollout_tc if tensor_cores else L.carenv_policy_rollout
     with torch.cuda.device(env.device):
-        rc = L.carenv_policy_rollout(env._handle, _p(packed), n, T, int(env_offset), int(seed) & (2 ** 64 - 1),
-                                     int(step0), _p(env.pos), _p(env.vel), _p(env.ints), _p(cur_obs), _p(cur_term),
-                                     _p(cur_trunc), float(env.reward_scaling), _p(buf.obs_buf), _p(buf.act_buf),
-                                     _p(buf.rew_buf), _p(buf.val_buf), _p(buf.term_buf), _p(buf.trunc_buf),
-                                     _p(buf.logprob_buf), _p(last_val), _p(u_dbg), env._stream())
-    _lib.check(rc, "carenv_policy_rollout")
+        rc = fn(env._handle, _p(packed), n, T, int(env_offset), int(seed) & (2 ** 64 - 1), int(step0), _p(env.pos),
+                _p(env.vel), _p(env.ints), _p(cur_obs), _p(cur_term), _p(cur_trunc), float(env.reward_scaling),
+                _p(buf.obs_buf), _p(buf.act_buf), _p(buf.rew_buf), _p(buf.val_buf), _p(buf.term_buf),
+                _p(buf.trunc_buf), _p(buf.logprob_buf), _p(last_val), _p(u_dbg), env._stream())
+    _lib.check(rc, "carenv_policy_rollout_tc" if tensor_cores else "carenv_policy_rollout")
     buf.ptr = T

@@ -28,8 +28,8 @@ def test_pack_layout_matches_header_constants():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [24, 1000])
-def test_fused_rollout_matches_torch_policy_and_env_kernel(tracks_dir, n):
+@pytest.mark.parametrize("n,tensor_cores", [(24, False), (1000, False), (24, True), (1000, True), (2049, True)])
+def test_fused_rollout_matches_torch_policy_and_env_kernel(tracks_dir, n, tensor_cores):
     dev = torch.device("cuda")
     path = os.path.join(tracks_dir, "big_track.json")
     T = 300
@@ -43,7 +43,8 @@ def test_fused_rollout_matches_torch_policy_and_env_kernel(tracks_dir, n):
     cur_obs = env.reset()[0].clone()
     cur_term, cur_trunc = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
     last_val, u = torch.empty(n, device=dev), torch.empty((T, n), device=dev)
-    packed = ppo_car_b200.pack_policy_weights(net.actor, net.critic)
+    pack = ppo_car_b200.pack_policy_weights_tc if tensor_cores else ppo_car_b200.pack_policy_weights
+    packed = pack(net.actor, net.critic)
     ppo_car_b200.fused_rollout(env, packed, buf, cur_obs, cur_term, cur_trunc, seed=11, step0=5, last_val=last_val, u_dbg=u)
     torch.cuda.synchronize()
     assert buf.ptr == T

@@ -141,9 +141,12 @@ def train(args) -> list[dict]:
 
     packed = last_val = None
     if args.fused_rollout:
-        from .policy import fused_rollout, pack_policy_weights
+        from .policy import fused_rollout, pack_policy_weights, pack_policy_weights_tc
 
-        packed = pack_policy_weights(agent.actor, agent.critic)
+        # tensor-core kernel (512-thread CTAs) once there are enough environments to fill the SMs,
+        # CUDA-core kernel (128-thread CTAs, lower latency) for small shards
+        pack_policy = pack_policy_weights_tc if n >= 65536 else pack_policy_weights
+        packed = pack_policy(agent.actor, agent.critic)
         last_val = torch.empty(n, device=dev)
 
     graph = None
@@ -166,7 +169,7 @@ def train(args) -> list[dict]:
         # ---- rollout
         with torch.no_grad():
             if packed is not None:
-                pack_policy_weights(agent.actor, agent.critic, out=packed)
+                pack_policy(agent.actor, agent.critic, out=packed)
                 fused_rollout(envs, packed, buf, next_obs, next_term, next_trunc, seed=args.seed,
                               step0=(epoch - 1) * T, env_offset=lo, last_val=last_val)
                 boot = last_val.reshape(1, -1)

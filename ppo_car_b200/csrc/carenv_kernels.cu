@@ -303,12 +303,13 @@ k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const
     const int w_off = (int)((tc::smem_u32(smem) + (uint32_t)table_bytes + 127u) / 128u * 128u - tc::smem_u32(smem));
     float *sw = reinterpret_cast<float *>(smem + w_off);
     unsigned char *sA = smem + w_off + ((kTcWeightFloats * 4 + 127) / 128 * 128);
-    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ __align__(8) unsigned long long mbar[kTcTiles];   // one "accumulator ready" barrier per 128-env group
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < kTcWeightFloats / 4; i += blockDim.x)
         reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(weights)[i];
-    if (tid == 0) tc::mbar_init(tc::smem_u32(&mbar), 1);
+    if (tid == 0)
+        for (int g = 0; g < kTcTiles; ++g) tc::mbar_init(tc::smem_u32(&mbar[g]), 1);
     if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
     const Tables T = stage_tables(G, P.n_gates, smem);      // ends with __syncthreads()
     tc::fence_async_smem();
@@ -386,10 +387,10 @@ k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const
                             tc::mma_tf32(d, tc::make_smem_desc(a0 + ks * 2 * tc::kLBO),
                                          tc::make_smem_desc(b0 + ks * 2 * tc::kLBO), idesc, (pr | ks) != 0);
                     }
-                }
-                tc::mma_commit(tc::smem_u32(&mbar));
+                    tc::mma_commit(tc::smem_u32(&mbar[g]));               // group g can start its epilogue while
+                }                                                          // the tensor core works on group g+1
             }
-            tc::mbar_wait(tc::smem_u32(&mbar), parity);
+            tc::mbar_wait(tc::smem_u32(&mbar[group]), parity);
             parity ^= 1u;
             tc::tc_fence_after();
             // (3) this thread's row of pre-activations: ReLU and the second layer

@@ -298,3 +298,41 @@ def test_api_errors_and_out_of_range_actions(tracks_dir):
         assert torch.equal(oa, ob) and torch.equal(ra, rb)
     env.close()
     env.close()                                               # idempotent
+
+
+def test_full_size_properties_1M_envs(tracks_dir):
+    """BASELINE config 4 width (1,048,576 envs): shard invariance against 8-way sharded replays of slices,
+    counter consistency, reset observation on done steps, and a 2,048-env slice against the float64 oracle."""
+    path = os.path.join(tracks_dir, "big_track.json")
+    n, T = 1_048_576, 64
+    g = torch.Generator(device="cuda").manual_seed(4)
+    acts = torch.randint(0, 9, (T, n), generator=g, device="cuda", dtype=torch.uint8)
+    env = ppo_car_b200.VecCarEnv(n, path)
+    env.reset()
+    out = env.rollout(acts, store_info=True)
+    done = (out["terminated"] | out["truncated"]).bool()
+    assert int(done.sum()) > 1_000
+    robs = torch.from_numpy(env.reset_observation).cuda()
+    assert torch.equal(out["obs"][done], robs.expand(int(done.sum()), 18))
+    tp = out["info"]["time_passed"]
+    prev = torch.cat([torch.zeros_like(tp[:1]), torch.where(done[:-1], torch.zeros_like(tp[:-1]), tp[:-1])])
+    assert torch.equal(tp, prev + 1)
+    from ppo_car_b200.shard import shard_range
+    for rank in (0, 3, 7):                                   # what ranks 0, 3 and 7 of an 8-GPU run would compute
+        lo, hi = shard_range(n, 8, rank)
+        sub = ppo_car_b200.VecCarEnv(hi - lo, path)
+        sub.reset()
+        so = sub.rollout(acts[:, lo:hi].contiguous(), store_info=True)
+        assert torch.equal(so["obs"], out["obs"][:, lo:hi]) and torch.equal(so["reward"], out["reward"][:, lo:hi])
+        assert torch.equal(so["terminated"], out["terminated"][:, lo:hi])
+        del sub, so
+    lo = n - 2048
+    ora = COracleVecEnv(2048, path, scan_all_gates=False)
+    ora.reset()
+    ref = ora.rollout(acts[:, lo:].cpu().numpy(), want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    got = dict(obs=out["obs"][:, lo:].cpu().numpy(), rew=out["reward"][:, lo:].cpu().numpy(),
+               term=out["terminated"][:, lo:].cpu().numpy(), trunc=out["truncated"][:, lo:].cpu().numpy(),
+               gates_passed=out["info"]["gates_passed"][:, lo:].cpu().numpy(),
+               time_passed=out["info"]["time_passed"][:, lo:].cpu().numpy(),
+               next_gate_index=out["info"]["next_gate_index"][:, lo:].cpu().numpy())
+    assert_trajectory_matches(got, ref, what="1M-env slice")

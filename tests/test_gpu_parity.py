@@ -336,3 +336,25 @@ def test_full_size_properties_1M_envs(tracks_dir):
                time_passed=out["info"]["time_passed"][:, lo:].cpu().numpy(),
                next_gate_index=out["info"]["next_gate_index"][:, lo:].cpu().numpy())
     assert_trajectory_matches(got, ref, what="1M-env slice")
+
+
+def test_adversarial_poses_on_gpu(tracks_dir):
+    """Rays within 1e-8..1e-4 px of vertices and cardinal hits at 10 px +- 1e-9..1e-4 (tests/adversarial.py):
+    states are written straight into the SoA tensors, one no-op step, flags and distances follow the oracle."""
+    from tests.adversarial import make_poses, oracle_at_poses
+
+    path = os.path.join(tracks_dir, "big_track.json")
+    poses, tr = make_poses(path, seed=9, per_item=120)
+    n = len(poses)
+    term_ref, fobs_ref = oracle_at_poses(path, poses, tr)
+    env = ppo_car_b200.VecCarEnv(n, path)
+    env.reset()
+    env.pos.copy_(torch.from_numpy(poses[:, :2].copy()))
+    env.ints[:, 0] = torch.from_numpy(poses[:, 2].astype(np.int32))
+    obs, rew, term, trunc, info = env.step(torch.full((n,), 8, device="cuda"))
+    term = term.cpu().numpy()
+    assert np.array_equal(term.astype(np.uint8), term_ref)
+    alive = term_ref == 0
+    assert_floats_close(obs.cpu().numpy()[alive][:, 6:], fobs_ref[alive][:, 6:], "ray distances at adversarial poses")
+    counts = env.slow_path_counts()
+    assert counts["line"] + counts["band"] > 500 and 0 < alive.sum() < n

@@ -90,3 +90,33 @@ def test_other_segment_counts_match_oracle(tmp_path, n_outer, n_inner):
                time_passed=e["info"][..., 1], next_gate_index=e["info"][..., 2])
     assert_trajectory_matches(got, ref, what=f"ring {n_outer}+{n_inner}")
     assert ref["term"].sum() > 50 and ref["gates_passed"].max() > 0
+
+
+def test_adversarial_poses_rays_through_vertices_and_at_the_collision_distance(tracks_dir):
+    """Poses constructed so that a ray passes within 1e-8 .. 1e-4 px of a polyline vertex, or a cardinal ray hits
+    a wall at 10 px +- 1e-9 .. 1e-4: far inside the float32 error (the guard bands are 1.5e-3 px and 2e-3
+    relative) but far outside float64 noise, so the oracle's answer is well defined and the float32 answer is
+    not.  The guard bands must send these to the float64 evaluation and every flag / distance must follow the
+    oracle.  (Offsets of exactly 0 are not used: there the float64 answer itself depends on the last bit of
+    cos/sin, which is the one thing oracle and kernel do not share.)"""
+    from tests.adversarial import make_poses, oracle_at_poses
+
+    path = os.path.join(tracks_dir, "big_track.json")
+    poses, tr = make_poses(path)
+    n = len(poses)
+    term_ref, fobs_ref = oracle_at_poses(path, poses, tr)
+    ref = {"term": [term_ref], "fobs": [fobs_ref]}
+    acts = np.full((1, n), 8, np.uint8)
+    pv = np.zeros((n, 4)); pv[:, 0], pv[:, 1] = poses[:, 0], poses[:, 1]
+    si = np.zeros((n, 4), np.int32); si[:, 0] = poses[:, 2].astype(np.int32)
+    e = emul_rollout(path, acts, state_pv=pv, state_i=si)
+    # the emulation's first step already evaluates the poked pose; compare with the oracle's first step
+    assert np.array_equal(e["term"][0], ref["term"][0])
+    alive = ref["term"][0] == 0
+    reset_obs = e["reset_obs"]
+    got = np.where(alive[:, None], e["obs"][0], 0.0)
+    want = np.where(alive[:, None], ref["fobs"][0], 0.0)
+    assert_floats_close(got[:, 6:], want[:, 6:], "ray distances at adversarial poses")
+    assert np.array_equal(e["obs"][0][~alive], np.broadcast_to(reset_obs, (int((~alive).sum()), 18)))
+    assert e["stats"][0] + e["stats"][1] > 200                # the float64 path really was exercised
+    assert 0 < alive.sum() < n

@@ -91,3 +91,34 @@ def test_training_with_fused_rollout_improves_reward():
     hist = train(args)
     assert all(math.isfinite(h["total_loss"]) for h in hist)
     assert hist[-1]["avg_reward"] > hist[0]["avg_reward"] + 0.03
+
+
+@pytest.mark.gpu
+def test_tcgen05_gemm_building_block():
+    """csrc/tc_mlp.cuh bring-up: D[128,256] = A[128,24] B[256,24]^T through tcgen05.mma kind::tf32 with the
+    accumulator in tensor memory and tcgen05.ld read-back, against float64 on TF32-exact inputs."""
+    import ctypes as C
+
+    from ppo_car_b200 import _lib
+    from ppo_car_b200.policy import _tf32
+
+    L = _lib.lib()
+    torch.manual_seed(0)
+    A = _tf32(torch.randn(128, 24, device="cuda"))
+    B = _tf32(torch.randn(256, 24, device="cuda"))
+    D = torch.full((128, 256), float("nan"), device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.carenv_tc_gemm_test(p(A), p(B), p(D), st), "carenv_tc_gemm_test")
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().T
+    assert (D.double() - ref).abs().max().item() < 2e-5       # float32 accumulation of 24 exact products
+    # structured probe: catches a wrong operand layout (row/column permutations) exactly
+    A2, B2 = torch.zeros(128, 24, device="cuda"), torch.zeros(256, 24, device="cuda")
+    A2[:, 0] = torch.arange(128, device="cuda").float()
+    B2[:, 0] = 1.0
+    A2[:, 21] = 1.0
+    B2[:, 21] = torch.arange(256, device="cuda").float() * 1024
+    _lib.check(L.carenv_tc_gemm_test(p(A2), p(B2), p(D), st), "carenv_tc_gemm_test")
+    torch.cuda.synchronize()
+    assert torch.equal(D, A2 @ B2.T)

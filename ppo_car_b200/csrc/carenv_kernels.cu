@@ -286,7 +286,7 @@ constexpr int kTcW2Off = 4 * kTcBFloats;                     // [actor hi | acto
 constexpr int kTcW2cOff = kTcW2Off + kHidden * 10;           // W2 actor as [j][5] pairs, then w2c[j]
 constexpr int kTcTailOff = kTcW2cOff + kHidden;              // b2[0..9], b2c, pad
 constexpr int kTcWeightFloats = kTcTailOff + 12;             // 27,404 floats
-constexpr int kTcThreads = kTcTiles * 128;
+constexpr int kTcThreads = kTcTiles * 128 + 32;            // four 128-env groups + one MMA-issuing warp
 
 template <int U>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -303,13 +303,19 @@ k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const
     const int w_off = (int)((tc::smem_u32(smem) + (uint32_t)table_bytes + 127u) / 128u * 128u - tc::smem_u32(smem));
     float *sw = reinterpret_cast<float *>(smem + w_off);
     unsigned char *sA = smem + w_off + ((kTcWeightFloats * 4 + 127) / 128 * 128);
-    __shared__ __align__(8) unsigned long long mbar[kTcTiles];   // one "accumulator ready" barrier per 128-env group
+    // per 128-env group: "accumulator ready" (MMA -> group), "accumulator consumed" and "operand rows written"
+    // (group -> MMA issuer).  Groups never wait for each other: no CTA-wide barrier inside the step loop.
+    __shared__ __align__(8) unsigned long long mbar_full[kTcTiles], mbar_cons[kTcTiles], mbar_rows[kTcTiles];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < kTcWeightFloats / 4; i += blockDim.x)
         reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(weights)[i];
     if (tid == 0)
-        for (int g = 0; g < kTcTiles; ++g) tc::mbar_init(tc::smem_u32(&mbar[g]), 1);
+        for (int g = 0; g < kTcTiles; ++g) {
+            tc::mbar_init(tc::smem_u32(&mbar_full[g]), 1);
+            tc::mbar_init(tc::smem_u32(&mbar_cons[g]), 128);
+            tc::mbar_init(tc::smem_u32(&mbar_rows[g]), 128);
+        }
     if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
     const Tables T = stage_tables(G, P.n_gates, smem);      // ends with __syncthreads()
     tc::fence_async_smem();
@@ -317,162 +323,183 @@ k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tbase = tmem_slot;
-    const int group = tid >> 7, row = tid & 127;
-    const uint32_t my_tmem = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(group * kTcCols);
-    unsigned char *myA = sA + group * 2 * tc::kABytes;       // hi tile, then lo tile
     const uint32_t sB = tc::smem_u32(sw);
-    uint32_t parity = 0;
-
-    const int e_raw = blockIdx.x * blockDim.x + tid;
-    const bool active = e_raw < n_envs;
-    const int e = active ? e_raw : n_envs - 1;               // idle threads shadow the last env (no stores)
-
-    EnvState s;
-    {
-        const double2 p = pos[e], v = vel[e];
-        const int4 q = ints[e];
-        s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
-        s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
-    }
-    float obs[kObsDim];
-    {
-        const float2 *src = reinterpret_cast<const float2 *>(cur_obs + (size_t)e * kObsDim);
-#pragma unroll
-        for (int i = 0; i < kObsDim / 2; ++i) { const float2 v = src[i]; obs[2 * i] = v.x; obs[2 * i + 1] = v.y; }
-    }
-    float tc_ = cur_term[e], uc = cur_trunc[e];
-    const uint32_t gid = (uint32_t)(env_offset + e);
     const uint32_t idesc = tc::make_idesc_tf32(128, kTcCols);
+    const int n_forward = n_steps + (last_val ? 1 : 0);      // forward passes per thread
 
-    // one forward pass of both nets for the observation in `obs`; every thread of the CTA must call it
-    auto forward = [&](PolicyOut &po) {
-        // (1) this thread's operand row: obs | 1 | 0...  split into TF32 hi and lo
-#pragma unroll
-        for (int c = 0; c < tc::kKChunks; ++c) {
-            float x[4], hi[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = 4 * c + j;
-                x[j] = k < kObsDim ? obs[k < kObsDim ? k : 0] : (k == kObsDim ? 1.0f : 0.0f);
-                hi[j] = tc::to_tf32(x[j]);
-                lo[j] = tc::to_tf32(x[j] - hi[j]);
-            }
-            const int off = tc::operand_offset(row, 4 * c);
-            *reinterpret_cast<float4 *>(myA + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4 *>(myA + tc::kABytes + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        tc::fence_async_smem();
-        float2 L[5];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) L[q] = make_float2(0.0f, 0.0f);
-        float2 V = make_float2(0.0f, 0.0f);
+    if (warp == kTcTiles * 4) {
+        // ===== MMA issuer (one elected lane): runs ahead of the groups, throttled only by the barriers =====
+        if ((tid & 31) == 0) {
+            uint32_t p_rows = 0, p_cons = 0;                 // same phase for every group: all advance in lock step here
+            for (int f = 0; f < n_forward; ++f) {
 #pragma unroll 1
-        for (int rnd = 0; rnd < 2 * kTcRounds; ++rnd) {
-            const int net = rnd / kTcRounds, part = rnd % kTcRounds;       // net 0 = actor, 1 = critic
-            tc::tc_fence_before();
-            __syncthreads();                                                // operands written / previous D consumed
-            if (tid == 0) {
+                for (int rnd = 0; rnd < 2 * kTcRounds; ++rnd) {
+                    const int net = rnd / kTcRounds, part = rnd % kTcRounds;
+                    const uint32_t bh = sB + (uint32_t)((2 * net) * kTcBFloats * 4 + part * (kTcCols / 8) * tc::kSBO);
+                    const uint32_t bl = bh + (uint32_t)(kTcBFloats * 4);
+#pragma unroll 1
+                    for (int g = 0; g < kTcTiles; ++g) {
+                        if (rnd == 0) tc::mbar_wait(tc::smem_u32(&mbar_rows[g]), p_rows);      // this step's rows
+                        if (f > 0 || rnd > 0) tc::mbar_wait(tc::smem_u32(&mbar_cons[g]), p_cons);  // D_g read out
+                        tc::tc_fence_after();
+                        const uint32_t ah = tc::smem_u32(sA + g * 2 * tc::kABytes), al = ah + tc::kABytes;
+                        const uint32_t d = tbase + (uint32_t)(g * kTcCols);
+#pragma unroll
+                        for (int pr = 0; pr < 3; ++pr) {
+                            const uint32_t a0 = (pr == 1) ? al : ah, b0 = (pr == 2) ? bl : bh;
+#pragma unroll
+                            for (int ks = 0; ks < tc::kK / 8; ++ks)
+                                tc::mma_tf32(d, tc::make_smem_desc(a0 + ks * 2 * tc::kLBO),
+                                             tc::make_smem_desc(b0 + ks * 2 * tc::kLBO), idesc, (pr | ks) != 0);
+                        }
+                        tc::mma_commit(tc::smem_u32(&mbar_full[g]));
+                    }
+                    if (rnd == 0) p_rows ^= 1u;
+                    if (f > 0 || rnd > 0) p_cons ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== environment threads: one thread = one environment = one TMEM lane of its group =====
+        const int group = tid >> 7, row = tid & 127;
+        const uint32_t my_tmem = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(group * kTcCols);
+        unsigned char *myA = sA + group * 2 * tc::kABytes;   // hi tile, then lo tile
+        const uint32_t full_bar = tc::smem_u32(&mbar_full[group]), cons_bar = tc::smem_u32(&mbar_cons[group]);
+        const uint32_t rows_bar = tc::smem_u32(&mbar_rows[group]);
+        uint32_t parity = 0;
+
+        const int e_raw = blockIdx.x * (kTcTiles * 128) + tid;
+        const bool active = e_raw < n_envs;
+        const int e = active ? e_raw : n_envs - 1;           // idle threads shadow the last env (no stores)
+
+        EnvState s;
+        {
+            const double2 p = pos[e], v = vel[e];
+            const int4 q = ints[e];
+            s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
+            s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
+        }
+        float obs[kObsDim];
+        {
+            const float2 *src = reinterpret_cast<const float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+            for (int i = 0; i < kObsDim / 2; ++i) { const float2 v = src[i]; obs[2 * i] = v.x; obs[2 * i + 1] = v.y; }
+        }
+        float tc_ = cur_term[e], uc = cur_trunc[e];
+        const uint32_t gid = (uint32_t)(env_offset + e);
+
+        // one forward pass of both nets for the observation in `obs`
+        auto forward = [&](PolicyOut &po) {
+            // this thread's operand row: obs | 1 | 0...  split into TF32 hi and lo.  The previous pass's MMAs have
+            // completed (their last "accumulator ready" was awaited), so the tile may be overwritten.
+#pragma unroll
+            for (int c = 0; c < tc::kKChunks; ++c) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 4 * c + j;
+                    const float x = k < kObsDim ? obs[k < kObsDim ? k : 0] : (k == kObsDim ? 1.0f : 0.0f);
+                    hi[j] = tc::to_tf32(x);
+                    lo[j] = tc::to_tf32(x - hi[j]);
+                }
+                const int off = tc::operand_offset(row, 4 * c);
+                *reinterpret_cast<float4 *>(myA + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(myA + tc::kABytes + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            tc::fence_async_smem();
+            tc::mbar_arrive(rows_bar);
+            float2 L[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) L[q] = make_float2(0.0f, 0.0f);
+            float2 V = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+            for (int rnd = 0; rnd < 2 * kTcRounds; ++rnd) {
+                const int net = rnd / kTcRounds, part = rnd % kTcRounds;   // net 0 = actor, 1 = critic
+                tc::mbar_wait(full_bar, parity);
+                parity ^= 1u;
                 tc::tc_fence_after();
-                const uint32_t bh = sB + (uint32_t)((2 * net) * kTcBFloats * 4 + part * (kTcCols / 8) * tc::kSBO);
-                const uint32_t bl = bh + (uint32_t)(kTcBFloats * 4);
+                if (net == 0) {
+                    const float2 *w2 = reinterpret_cast<const float2 *>(sw + kTcW2Off) + (size_t)(part * kTcCols) * 5;
 #pragma unroll 1
-                for (int g = 0; g < kTcTiles; ++g) {
-                    const uint32_t ah = tc::smem_u32(sA + g * 2 * tc::kABytes), al = ah + tc::kABytes;
-                    const uint32_t d = tbase + (uint32_t)(g * kTcCols);
+                    for (int c = 0; c < kTcCols; c += 16) {
+                        float v[16];
+                        tc::tmem_ld16(my_tmem + c, v);
+                        if (c + 16 == kTcCols) { tc::tc_fence_before(); tc::mbar_arrive(cons_bar); }   // D_g is free again
 #pragma unroll
-                    for (int pr = 0; pr < 3; ++pr) {
-                        const uint32_t a0 = (pr == 1) ? al : ah, b0 = (pr == 2) ? bl : bh;
+                        for (int i = 0; i < 16; ++i) {
+                            const float h = fmaxf(v[i], 0.0f);
 #pragma unroll
-                        for (int ks = 0; ks < tc::kK / 8; ++ks)
-                            tc::mma_tf32(d, tc::make_smem_desc(a0 + ks * 2 * tc::kLBO),
-                                         tc::make_smem_desc(b0 + ks * 2 * tc::kLBO), idesc, (pr | ks) != 0);
+                            for (int q = 0; q < 5; ++q) L[q] = __ffma2_rn(make_float2(h, h), w2[(c + i) * 5 + q], L[q]);
+                        }
                     }
-                    tc::mma_commit(tc::smem_u32(&mbar[g]));               // group g can start its epilogue while
-                }                                                          // the tensor core works on group g+1
-            }
-            tc::mbar_wait(tc::smem_u32(&mbar[group]), parity);
-            parity ^= 1u;
-            tc::tc_fence_after();
-            // (3) this thread's row of pre-activations: ReLU and the second layer
-            if (net == 0) {
-                const float2 *w2 = reinterpret_cast<const float2 *>(sw + kTcW2Off) + (size_t)(part * kTcCols) * 5;
+                } else {
+                    const float4 *wc = reinterpret_cast<const float4 *>(sw + kTcW2cOff + part * kTcCols);
 #pragma unroll 1
-                for (int c = 0; c < kTcCols; c += 16) {
-                    float v[16];
-                    tc::tmem_ld16(my_tmem + c, v);
+                    for (int c = 0; c < kTcCols; c += 16) {
+                        float v[16];
+                        tc::tmem_ld16(my_tmem + c, v);
+                        if (c + 16 == kTcCols) { tc::tc_fence_before(); tc::mbar_arrive(cons_bar); }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float h = fmaxf(v[i], 0.0f);
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) L[q] = __ffma2_rn(make_float2(h, h), w2[(c + i) * 5 + q], L[q]);
-                    }
-                }
-            } else {
-                const float4 *wc = reinterpret_cast<const float4 *>(sw + kTcW2cOff + part * kTcCols);
-#pragma unroll 1
-                for (int c = 0; c < kTcCols; c += 16) {
-                    float v[16];
-                    tc::tmem_ld16(my_tmem + c, v);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 w4 = wc[c / 4 + i];
-                        V = __ffma2_rn(make_float2(fmaxf(v[4 * i], 0.0f), fmaxf(v[4 * i + 1], 0.0f)),
-                                       make_float2(w4.x, w4.y), V);
-                        V = __ffma2_rn(make_float2(fmaxf(v[4 * i + 2], 0.0f), fmaxf(v[4 * i + 3], 0.0f)),
-                                       make_float2(w4.z, w4.w), V);
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 w4 = wc[c / 4 + i];
+                            V = __ffma2_rn(make_float2(fmaxf(v[4 * i], 0.0f), fmaxf(v[4 * i + 1], 0.0f)),
+                                           make_float2(w4.x, w4.y), V);
+                            V = __ffma2_rn(make_float2(fmaxf(v[4 * i + 2], 0.0f), fmaxf(v[4 * i + 3], 0.0f)),
+                                           make_float2(w4.z, w4.w), V);
+                        }
                     }
                 }
             }
-        }
-        const float *tail = sw + kTcTailOff;
+            const float *tail = sw + kTcTailOff;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            po.logit[2 * q] = L[q].x + tail[2 * q];
-            po.logit[2 * q + 1] = L[q].y + tail[2 * q + 1];
-        }
-        po.value = (V.x + V.y) + tail[10];
-    };
+            for (int q = 0; q < 5; ++q) {
+                po.logit[2 * q] = L[q].x + tail[2 * q];
+                po.logit[2 * q + 1] = L[q].y + tail[2 * q + 1];
+            }
+            po.value = (V.x + V.y) + tail[10];
+        };
 
-    PolicyOut po;
-    for (int t = 0; t < n_steps; ++t) {
-        const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
-        forward(po);
-        const unsigned long long gs = step0 + (unsigned long long)t;
-        const uint32_t bits = philox_uniform_bits((uint32_t)seed, (uint32_t)(seed >> 32), gid, (uint32_t)gs,
-                                                  (uint32_t)(gs >> 32), 0x43415245u);
-        const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
-        float logp, us;
-        const int a = sample_action(po, u, logp, us);
+        PolicyOut po;
+        for (int t = 0; t < n_steps; ++t) {
+            const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+            forward(po);
+            const unsigned long long gs = step0 + (unsigned long long)t;
+            const uint32_t bits = philox_uniform_bits((uint32_t)seed, (uint32_t)(seed >> 32), gid, (uint32_t)gs,
+                                                      (uint32_t)(gs >> 32), 0x43415245u);
+            const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
+            float logp, us;
+            const int a = sample_action(po, u, logp, us);
+            if (active) {
+                float2 *dst = reinterpret_cast<float2 *>(obs_buf + idx * kObsDim);
+#pragma unroll
+                for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+                act_buf[idx] = (float)a;
+                val_buf[idx] = po.value;
+                logp_buf[idx] = logp;
+                term_buf[idx] = tc_;
+                trunc_buf[idx] = uc;
+                if (u_dbg) u_dbg[idx] = u;
+            }
+            StepResult o;
+            env_step<U>(s, a, reward_scale, P, T, o, active ? stats : nullptr);
+            if (active) rew_buf[idx] = o.reward;
+#pragma unroll
+            for (int i = 0; i < kObsDim; ++i) obs[i] = o.obs[i];
+            tc_ = o.terminated ? 1.0f : 0.0f;
+            uc = o.truncated ? 1.0f : 0.0f;
+        }
+        if (last_val) forward(po);                           // bootstrap value of the final observation
         if (active) {
-            float2 *dst = reinterpret_cast<float2 *>(obs_buf + idx * kObsDim);
+            pos[e] = make_double2(s.px, s.py);
+            vel[e] = make_double2(s.vx, s.vy);
+            ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+            float2 *dst = reinterpret_cast<float2 *>(cur_obs + (size_t)e * kObsDim);
 #pragma unroll
             for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
-            act_buf[idx] = (float)a;
-            val_buf[idx] = po.value;
-            logp_buf[idx] = logp;
-            term_buf[idx] = tc_;
-            trunc_buf[idx] = uc;
-            if (u_dbg) u_dbg[idx] = u;
+            cur_term[e] = tc_;
+            cur_trunc[e] = uc;
+            if (last_val) last_val[e] = po.value;
         }
-        StepResult o;
-        env_step<U>(s, a, reward_scale, P, T, o, active ? stats : nullptr);
-        if (active) rew_buf[idx] = o.reward;
-#pragma unroll
-        for (int i = 0; i < kObsDim; ++i) obs[i] = o.obs[i];
-        tc_ = o.terminated ? 1.0f : 0.0f;
-        uc = o.truncated ? 1.0f : 0.0f;
-    }
-    if (last_val) forward(po);                               // bootstrap value (all threads take part in the MMA)
-    if (active) {
-        pos[e] = make_double2(s.px, s.py);
-        vel[e] = make_double2(s.vx, s.vy);
-        ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
-        float2 *dst = reinterpret_cast<float2 *>(cur_obs + (size_t)e * kObsDim);
-#pragma unroll
-        for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
-        cur_term[e] = tc_;
-        cur_trunc[e] = uc;
-        if (last_val) last_val[e] = po.value;
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -806,7 +833,7 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
     const size_t smem = (size_t)table_bytes + 128 + (size_t)((kTcWeightFloats * 4 + 127) / 128 * 128) +
                         (size_t)kTcTiles * 2 * tc::kABytes;
     if (smem > 227 * 1024) return fail(CARENV_E_TRACK, "track tables too large for the tensor-core rollout kernel");
-    const int grid = (n_envs + kTcThreads - 1) / kTcThreads;
+    const int grid = (n_envs + kTcTiles * 128 - 1) / (kTcTiles * 128);
     int U = h->force_generic ? 1 : h->host.P.unroll;
     if (h->max_unroll > 0 && U > h->max_unroll) U = h->max_unroll;
     auto launch = [&](auto kern) -> int {

@@ -63,6 +63,10 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar_smem, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(mbar_smem), "r"(count) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar_smem) {
+    asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.shared::cta.b64 t, [%0];\n\t}\n" :: "r"(mbar_smem) : "memory");
+}
+
 // Bounded wait: a wrong descriptor must not hang the GPU box — trap instead.
 __device__ __forceinline__ void mbar_wait(uint32_t mbar_smem, uint32_t parity) {
     uint32_t done = 0;

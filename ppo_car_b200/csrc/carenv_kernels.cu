@@ -75,12 +75,13 @@ template <> __device__ __forceinline__ uint8_t make_flag<uint8_t>(int v) { retur
 template <> __device__ __forceinline__ float make_flag<float>(int v) { return v ? 1.0f : 0.0f; }
 
 // Stage the per-thread-indexed tables into shared memory (all sizes are multiples of 8 bytes).
-__device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, unsigned char *smem) {
+__device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, int n_seg, unsigned char *smem) {
     D2 *s_trig64 = reinterpret_cast<D2 *>(smem);
     D2 *s_acc64 = s_trig64 + kHeadings;
     GateRec *s_gates = reinterpret_cast<GateRec *>(s_acc64 + kHeadings);
     F2 *s_trig32 = reinterpret_cast<F2 *>(s_gates + n_gates);
-    const int n64a = kHeadings * 2, n64g = n_gates * (int)(sizeof(GateRec) / 8);
+    double *s_walls = reinterpret_cast<double *>(s_trig32 + kHeadings);   // float64 walls for the exact path: a
+    const int n64a = kHeadings * 2, n64g = n_gates * (int)(sizeof(GateRec) / 8);   // global-memory copy costs ~10 k cycles per fallback
     double *d0 = reinterpret_cast<double *>(s_trig64);
     double *d1 = reinterpret_cast<double *>(s_acc64);
     double *d2 = reinterpret_cast<double *>(s_gates);
@@ -92,8 +93,9 @@ __device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, uns
     for (int i = threadIdx.x; i < n64a; i += blockDim.x) { d0[i] = g0[i]; d1[i] = g1[i]; }
     for (int i = threadIdx.x; i < n64g; i += blockDim.x) d2[i] = g2[i];
     for (int i = threadIdx.x; i < kHeadings; i += blockDim.x) d3[i] = g3[i];
+    for (int i = threadIdx.x; i < 4 * n_seg; i += blockDim.x) s_walls[i] = G.walls64[i];
     __syncthreads();
-    return Tables{s_trig32, s_trig64, s_acc64, s_gates, G.walls64};
+    return Tables{s_trig32, s_trig64, s_acc64, s_gates, s_walls};
 }
 
 #ifndef CARENV_MIN_BLOCKS
@@ -106,7 +108,7 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
           float *__restrict__ obs_out, float *__restrict__ rew_out, FlagT *__restrict__ term_out,
           FlagT *__restrict__ trunc_out, int4 *__restrict__ info_out, unsigned long long *stats) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const Tables T = stage_tables(G, P.n_gates, smem);
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_envs) return;
 
@@ -206,7 +208,7 @@ k_policy_rollout(const __grid_constant__ TrackParams P, const Tables G, const fl
     float *sw = reinterpret_cast<float *>(smem + table_bytes);
     for (int i = threadIdx.x; i < kPolicyFloats / 4; i += blockDim.x)
         reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(weights)[i];
-    const Tables T = stage_tables(G, P.n_gates, smem);      // ends with __syncthreads()
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);      // ends with __syncthreads()
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_envs) return;
 
@@ -317,7 +319,7 @@ k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const
             tc::mbar_init(tc::smem_u32(&mbar_rows[g]), 128);
         }
     if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
-    const Tables T = stage_tables(G, P.n_gates, smem);      // ends with __syncthreads()
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);      // ends with __syncthreads()
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -692,7 +694,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     const size_t b_gates = sizeof(GateRec) * (size_t)n_gates, b_trig32 = sizeof(F2) * kHeadings;
     const size_t b_walls = sizeof(double) * 4 * (size_t)n_walls;
     const size_t o_acc = b_trig64, o_gates = o_acc + b_acc, o_trig32 = o_gates + b_gates, o_walls = o_trig32 + b_trig32;
-    h->smem_bytes = o_walls;   // everything except the float64 walls is staged to shared memory
+    h->smem_bytes = o_walls + b_walls;   // the whole blob is staged to shared memory
     cudaError_t e = cudaMalloc(&h->d_blob, o_walls + b_walls);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_stats, sizeof(unsigned long long) * kNumStats);
     if (e == cudaSuccess) e = cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * kNumStats);

@@ -36,7 +36,7 @@ extern "C" {
 #define CARENV_ABI_VERSION 1
 #define CARENV_OBS_DIM 18      /* 6 + num_rays, lib/car_env.py:513-519 */
 #define CARENV_NUM_ACTIONS 9   /* spaces.Discrete(9), lib/car_env.py:525 */
-#define CARENV_MAX_SEGMENTS 128
+#define CARENV_MAX_SEGMENTS 2048   /* up to 128: geometry as kernel constants (fast kernels); above: staged in shared memory */
 
 #define CARENV_E_INVAL (-1)    /* bad argument (null pointer, size, dtype) */
 #define CARENV_E_TRACK (-2)    /* track does not fit (too many segments) or is malformed */

@@ -44,7 +44,8 @@ namespace carenv {
 constexpr int kNumRays = 12;
 constexpr int kObsDim = 18;
 constexpr int kHeadings = 72;      // 360 / 5 degrees
-constexpr int kMaxSeg = 128;       // wall segments carried in kernel-parameter space
+constexpr int kMaxSeg = 128;       // wall segments carried in kernel-parameter space (fast kernels)
+constexpr int kMaxBigSeg = 2048;   // larger tracks: geometry staged in shared memory, generic loop (U = 0)
 constexpr int kTimeLimit = 1000;   // lib/car_env.py:491
 
 struct F2 { float x, y; };
@@ -68,7 +69,8 @@ struct TrackParams {
     float tiny_d;       // distances below this are re-evaluated (sign of u uncertain)
     float gate_band;    // gate margin band, in units of the gate length
     float tiny_un;      // |cross(e, A')| below this: every line is re-evaluated
-    int unroll;         // largest U in {4, 2, 1} such that n_seg and every polyline start are multiples of U
+    int unroll;         // largest U in {4, 2, 1} such that n_seg and every polyline start are multiples of U;
+                        // 0 for tracks with more than kMaxSeg segments (geometry from Tables::segf/segd)
     int pad2[2];
     double start_x, start_y;
     float reset_obs[kObsDim];
@@ -85,6 +87,8 @@ struct Tables {
     const D2 *acc64;         // [72] (cos*0.8, sin*0.8), float64  (lib/car_env.py:430)
     const GateRec *gates;    // [n_gates]
     const double *walls64;   // [n_seg][4] x1 y1 x2 y2 — only read on the exact path
+    const SegF *segf;        // [n_seg] only for tracks with more than kMaxSeg segments (else null: the
+    const SegD *segd;        //         geometry is in TrackParams, i.e. constant-bank operands)
 };
 
 struct EnvState {
@@ -404,10 +408,20 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
 #pragma unroll
         for (int l = 0; l < 6; ++l) { w.Rp[l] = R0; w.Rm[l] = -R0; w.gq[l] = 1.0e30f; w.qa[l] = 0.0f; }
         w.gu = 1.0e30f;
+        if (U == 0) {                                        // big track: geometry from shared memory
 #pragma unroll 1
-        for (int j = 0; j < P.n_seg; ++j) {
-            if (P.segf[j].chain_start) wall_chain_start(w, P.segf[j]);
-            wall_segment<1>(w, P.segf[j], P.segd[j], s.px, s.py);
+            for (int j = 0; j < P.n_seg; ++j) {
+                const SegF f = T.segf[j];
+                const SegD g = T.segd[j];
+                if (f.chain_start) wall_chain_start(w, f);
+                wall_segment<1>(w, f, g, s.px, s.py);
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < P.n_seg; ++j) {
+                if (P.segf[j].chain_start) wall_chain_start(w, P.segf[j]);
+                wall_segment<1>(w, P.segf[j], P.segd[j], s.px, s.py);
+            }
         }
 #pragma unroll
         for (int l = 0; l < 6; ++l) { Rp[l] = w.Rp[l]; Rm[l] = w.Rm[l]; gq[l] = w.gq[l]; }

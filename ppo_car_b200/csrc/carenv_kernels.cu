@@ -44,7 +44,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 struct Handle {
     int device;
     HostTrack host;
-    unsigned char *d_blob;    // trig64 | acc64 | gates | trig32 | walls64
+    unsigned char *d_blob;    // trig64 | acc64 | gates | trig32 | walls64 | segf | segd
     Tables dev;               // device pointers into d_blob
     unsigned long long *d_stats;
     size_t smem_bytes;
@@ -94,8 +94,18 @@ __device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, int
     for (int i = threadIdx.x; i < n64g; i += blockDim.x) d2[i] = g2[i];
     for (int i = threadIdx.x; i < kHeadings; i += blockDim.x) d3[i] = g3[i];
     for (int i = threadIdx.x; i < 4 * n_seg; i += blockDim.x) s_walls[i] = G.walls64[i];
+    const SegF *s_segf = nullptr;
+    const SegD *s_segd = nullptr;
+    if (n_seg > kMaxSeg) {                                  // big track: the segment records live in shared memory too
+        double *d4 = s_walls + 4 * n_seg, *d5 = d4 + 4 * n_seg;            // SegF = 4 doubles, SegD = 3 doubles
+        const double *g4 = reinterpret_cast<const double *>(G.segf), *g5 = reinterpret_cast<const double *>(G.segd);
+        for (int i = threadIdx.x; i < 4 * n_seg; i += blockDim.x) d4[i] = g4[i];
+        for (int i = threadIdx.x; i < 3 * n_seg; i += blockDim.x) d5[i] = g5[i];
+        s_segf = reinterpret_cast<const SegF *>(d4);
+        s_segd = reinterpret_cast<const SegD *>(d5);
+    }
     __syncthreads();
-    return Tables{s_trig32, s_trig64, s_acc64, s_gates, s_walls};
+    return Tables{s_trig32, s_trig64, s_acc64, s_gates, s_walls, s_segf, s_segd};
 }
 
 #ifndef CARENV_MIN_BLOCKS
@@ -629,9 +639,11 @@ int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel,
                    int32_t *info_out, cudaStream_t stream) {
     int U = h->force_generic ? 1 : h->host.P.unroll;
     if (h->max_unroll > 0 && U > h->max_unroll) U = h->max_unroll;
+    if (h->host.P.n_seg > kMaxSeg) U = 0;                   // geometry from shared memory
 #define ARGS h, n_envs, n_steps, pos, vel, ints, actions, reward_scale, obs_out, reward_out, term_out, trunc_out, info_out, stream
     if (U == 4) return launch_rollout_t<ActT, FlagT, 4>(ARGS);
     if (U == 2) return launch_rollout_t<ActT, FlagT, 2>(ARGS);
+    if (U == 0) return launch_rollout_t<ActT, FlagT, 0>(ARGS);
     return launch_rollout_t<ActT, FlagT, 1>(ARGS);
 #undef ARGS
 }
@@ -676,6 +688,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (!walls || !gates) return fail(CARENV_E_INVAL, "null geometry pointer");
     if (n_walls < 1 || n_walls > CARENV_MAX_SEGMENTS)
         return fail(CARENV_E_TRACK, "number of wall segments must be in 1.." + std::to_string(CARENV_MAX_SEGMENTS));
+    static_assert(CARENV_MAX_SEGMENTS == kMaxBigSeg, "header and kernel limits differ");
     if (n_gates < 1 || n_gates > 4000) return fail(CARENV_E_TRACK, "number of gates must be in 1..4000");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1) return fail(CARENV_E_NOGPU, "no CUDA device");
@@ -692,9 +705,14 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     const size_t b_trig64 = sizeof(D2) * kHeadings, b_acc = sizeof(D2) * kHeadings;
     const size_t b_gates = sizeof(GateRec) * (size_t)n_gates, b_trig32 = sizeof(F2) * kHeadings;
     const size_t b_walls = sizeof(double) * 4 * (size_t)n_walls;
+    const size_t b_segf = sizeof(SegF) * (size_t)n_walls, b_segd = sizeof(SegD) * (size_t)n_walls;
     const size_t o_acc = b_trig64, o_gates = o_acc + b_acc, o_trig32 = o_gates + b_gates, o_walls = o_trig32 + b_trig32;
-    h->smem_bytes = o_walls + b_walls;   // the whole blob is staged to shared memory
-    cudaError_t e = cudaMalloc(&h->d_blob, o_walls + b_walls);
+    const size_t o_segf = o_walls + b_walls, o_segd = o_segf + b_segf;
+    const bool big = n_walls > kMaxSeg;
+    // staged to shared memory: everything up to the walls, plus the segment records for big tracks
+    h->smem_bytes = big ? o_segd + b_segd : o_walls + b_walls;
+    if (h->smem_bytes > 200 * 1024) { delete h; return fail(CARENV_E_TRACK, "track tables do not fit in shared memory"); }
+    cudaError_t e = cudaMalloc(&h->d_blob, o_segd + b_segd);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_stats, sizeof(unsigned long long) * kNumStats);
     if (e == cudaSuccess) e = cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * kNumStats);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob, h->host.trig64.data(), b_trig64, cudaMemcpyHostToDevice);
@@ -702,6 +720,8 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_gates, h->host.gates.data(), b_gates, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_trig32, h->host.trig32.data(), b_trig32, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_walls, h->host.walls64.data(), b_walls, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_segf, h->host.segf.data(), b_segf, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_segd, h->host.segd.data(), b_segd, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         cudaFree(h->d_blob); cudaFree(h->d_stats);
         delete h;
@@ -712,6 +732,8 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     h->dev.gates = reinterpret_cast<const GateRec *>(h->d_blob + o_gates);
     h->dev.trig32 = reinterpret_cast<const F2 *>(h->d_blob + o_trig32);
     h->dev.walls64 = reinterpret_cast<const double *>(h->d_blob + o_walls);
+    h->dev.segf = reinterpret_cast<const SegF *>(h->d_blob + o_segf);
+    h->dev.segd = reinterpret_cast<const SegD *>(h->d_blob + o_segd);
     *handle = h;
     return 0;
 }
@@ -780,6 +802,8 @@ int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs,
     if (!packed_weights || !pos || !vel || !ints || !cur_obs || !cur_term || !cur_trunc || !obs_buf || !act_buf ||
         !rew_buf || !val_buf || !term_buf || !trunc_buf || !logp_buf)
         return fail(CARENV_E_INVAL, "null pointer");
+    if (h->host.P.n_seg > kMaxSeg)
+        return fail(CARENV_E_TRACK, "the fused rollout kernels support tracks with at most 128 wall segments");
     DeviceGuard guard(h->device);
     if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
     const int table_bytes = (int)((h->smem_bytes + 15) / 16 * 16);
@@ -828,6 +852,8 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
     if (!packed_weights || !pos || !vel || !ints || !cur_obs || !cur_term || !cur_trunc || !obs_buf || !act_buf ||
         !rew_buf || !val_buf || !term_buf || !trunc_buf || !logp_buf)
         return fail(CARENV_E_INVAL, "null pointer");
+    if (h->host.P.n_seg > kMaxSeg)
+        return fail(CARENV_E_TRACK, "the fused rollout kernels support tracks with at most 128 wall segments");
     DeviceGuard guard(h->device);
     if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
     const int table_bytes = (int)h->smem_bytes;

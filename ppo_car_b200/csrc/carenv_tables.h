@@ -19,13 +19,17 @@ struct HostTrack {
     std::vector<D2> trig64, acc64;
     std::vector<GateRec> gates;
     std::vector<double> walls64;
-    Tables tables() const { return Tables{trig32.data(), trig64.data(), acc64.data(), gates.data(), walls64.data()}; }
+    std::vector<SegF> segf;      // every segment (TrackParams only holds them up to kMaxSeg)
+    std::vector<SegD> segd;
+    Tables tables() const {
+        return Tables{trig32.data(), trig64.data(), acc64.data(), gates.data(), walls64.data(), segf.data(), segd.data()};
+    }
 };
 
 // returns 0 on success, <0 on invalid input
 inline int build_host_track(const double *walls, int n_walls, const double *gates, int n_gates,
                             double sx, double sy, double angle_deg, HostTrack &H) {
-    if (n_walls < 1 || n_walls > kMaxSeg || n_gates < 1 || !walls || !gates) return -1;
+    if (n_walls < 1 || n_walls > kMaxBigSeg || n_gates < 1 || !walls || !gates) return -1;
     memset(&H.P, 0, sizeof(H.P));
     TrackParams &P = H.P;
     P.n_seg = n_walls; P.n_gates = n_gates;
@@ -42,15 +46,18 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
     }
 
     H.walls64.assign(walls, walls + 4 * (size_t)n_walls);
+    H.segf.resize(n_walls);
+    H.segd.resize(n_walls);
     double min_sin = 1.0;
     for (int j = 0; j < n_walls; ++j) {
         const double ax = walls[4 * j], ay = walls[4 * j + 1], bx = walls[4 * j + 2], by = walls[4 * j + 3];
-        SegF &f = P.segf[j];
+        SegF &f = H.segf[j];
         f.ahx = (float)ax; f.ahy = (float)ay; f.bhx = (float)bx; f.bhy = (float)by;
         const double ex = bx - ax, ey = by - ay;
         f.ex = (float)ex; f.ey = (float)ey; f.ney = -f.ey;
         f.chain_start = (j == 0 || walls[4 * j - 2] != ax || walls[4 * j - 1] != ay) ? 1 : 0;
-        P.segd[j] = SegD{fma(ex, ay, -(ey * ax)), ex, ey};
+        H.segd[j] = SegD{fma(ex, ay, -(ey * ax)), ex, ey};
+        if (n_walls <= kMaxSeg) { P.segf[j] = H.segf[j]; P.segd[j] = H.segd[j]; }
         const double len = hypot(ex, ey);
         if (len > 0)
             for (int k = 0; k < kHeadings; ++k) {
@@ -75,11 +82,11 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
     P.gate_band = 2.0e-3f;
     P.tiny_un = 1.0e-3f;    // float64 error of cross(e, A - pos) is ~1e-10: relative error < 1e-7 above this
     // loop unrolling the track allows (see cast_walls)
-    P.unroll = 1;
-    for (int U = 4; U >= 2; U /= 2) {
+    P.unroll = (n_walls <= kMaxSeg) ? 1 : 0;
+    for (int U = 4; U >= 2 && n_walls <= kMaxSeg; U /= 2) {
         bool ok = (n_walls % U == 0);
         for (int j = 0; j < n_walls && ok; ++j)
-            if (P.segf[j].chain_start && j % U != 0) ok = false;
+            if (H.segf[j].chain_start && j % U != 0) ok = false;
         if (ok) { P.unroll = U; break; }
     }
 

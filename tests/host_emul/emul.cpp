@@ -28,8 +28,9 @@ extern "C" int emul_rollout(const double *walls, int n_walls, const double *gate
         for (int t = 0; t < T; ++t) {
             const size_t k = (size_t)t * n_envs + e;
             StepResult o;
-            const int U = unrolled ? H.P.unroll : 1;
-            if (U == 4) env_step<4>(s, actions[k], reward_scale, H.P, Tb, o, stats);
+            const int U = H.P.n_seg > kMaxSeg ? 0 : (unrolled ? H.P.unroll : 1);
+            if (U == 0) env_step<0>(s, actions[k], reward_scale, H.P, Tb, o, stats);
+            else if (U == 4) env_step<4>(s, actions[k], reward_scale, H.P, Tb, o, stats);
             else if (U == 2) env_step<2>(s, actions[k], reward_scale, H.P, Tb, o, stats);
             else env_step<1>(s, actions[k], reward_scale, H.P, Tb, o, stats);
             if (obs) for (int i = 0; i < kObsDim; ++i) obs[k * kObsDim + i] = o.obs[i];

@@ -41,9 +41,9 @@ def test_bad_arguments_return_error_codes():
     L = _lib.lib()
     h = C.c_void_p()
     assert L.carenv_create(None, 4, None, 1, 0.0, 0.0, 0.0, 0, C.byref(h)) == -1          # CARENV_E_INVAL
-    walls = np.zeros((200, 4))
+    walls = np.zeros((3000, 4))
     gates = np.zeros((1, 4))
-    rc = L.carenv_create(walls.ctypes.data_as(C.c_void_p), 200, gates.ctypes.data_as(C.c_void_p), 1, 0.0, 0.0, 0.0,
+    rc = L.carenv_create(walls.ctypes.data_as(C.c_void_p), 3000, gates.ctypes.data_as(C.c_void_p), 1, 0.0, 0.0, 0.0,
                          0, C.byref(h))
     assert rc == -2 and b"segments" in L.carenv_last_error()                               # CARENV_E_TRACK
     assert L.carenv_step(None, 1, None, None, None, None, 0, 1.0, None, None, None, None, 0, None, None) < 0

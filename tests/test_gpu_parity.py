@@ -257,8 +257,9 @@ def test_config3_size_integer_traces_bit_exact(tracks_dir):
 
 
 def test_limits_many_gates_and_max_segments(tmp_path):
-    """128 wall segments (the parameter-space limit) and 1,500 gates (gate table > 48 KB of shared memory,
-    which needs the opt-in dynamic shared memory attribute); one more segment is rejected with an error."""
+    """128 wall segments (the limit of the constant-bank kernels) with 1,500 gates (gate table > 48 KB of shared
+    memory: opt-in dynamic shared memory attribute); 129 and 400 segments run the shared-memory-geometry kernel;
+    more than 2,048 segments are rejected with an error."""
     from tests.synth_tracks import ring_track
 
     path = ring_track(str(tmp_path / "big_ring.json"), 64, 64, n_gates=1500, wobble=0.03)
@@ -272,7 +273,17 @@ def test_limits_many_gates_and_max_segments(tmp_path):
     out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
     assert_trajectory_matches(_gpu_traj(out), ref, what="64+64 segments, 1500 gates")
     assert ref["gates_passed"].max() > 20
-    too_big = ring_track(str(tmp_path / "too_big.json"), 65, 64)
+    for n_outer, n_inner in ((65, 64), (230, 170)):
+        big = ring_track(str(tmp_path / f"ring_{n_outer}.json"), n_outer, n_inner, n_gates=40, wobble=0.03)
+        ora = COracleVecEnv(256, big, scan_all_gates=False)
+        ora.reset()
+        ref = ora.rollout(acts[:, :256], want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+        env = ppo_car_b200.VecCarEnv(256, big)
+        env.reset()
+        out = env.rollout(torch.from_numpy(acts[:, :256].copy()).cuda(), store_info=True)
+        assert_trajectory_matches(_gpu_traj(out), ref, what=f"{n_outer}+{n_inner} segments (shared-memory geometry)")
+        assert ref["term"].sum() > 20
+    too_big = ring_track(str(tmp_path / "too_big.json"), 1500, 549)
     with pytest.raises(ppo_car_b200.CarEnvError, match="segments"):
         ppo_car_b200.VecCarEnv(8, too_big)
 

@@ -74,7 +74,7 @@ def test_packed_and_scalar_wall_paths_are_bit_identical(tracks_dir):
         assert np.array_equal(a["stats"], b["stats"])
 
 
-@pytest.mark.parametrize("n_outer,n_inner", [(7, 5), (10, 6), (16, 12), (31, 29)])
+@pytest.mark.parametrize("n_outer,n_inner", [(7, 5), (10, 6), (16, 12), (31, 29), (90, 80)])
 def test_other_segment_counts_match_oracle(tmp_path, n_outer, n_inner):
     """Tracks with other polyline sizes pick other loop unrollings (1, 2, 4): all must follow the oracle."""
     from tests.synth_tracks import ring_track

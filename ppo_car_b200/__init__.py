@@ -7,9 +7,9 @@ Public surface (mirrors what the reference's train.py uses):
 """
 from ._lib import CarEnvError, build
 from .buffer import Buffer, gae_reverse_scan
-from .track import Track, builtin_track, load_track
-from .vec_env import VecCarEnv
+from .track import Track, builtin_track, load_track, validate_track
+from .vec_env import MultiTrackVecEnv, VecCarEnv
 from .policy import fused_rollout, pack_policy_weights, pack_policy_weights_tc
 
-__all__ = ["VecCarEnv", "Buffer", "gae_reverse_scan", "load_track", "builtin_track", "Track", "build", "CarEnvError",
+__all__ = ["VecCarEnv", "MultiTrackVecEnv", "validate_track", "Buffer", "gae_reverse_scan", "load_track", "builtin_track", "Track", "build", "CarEnvError",
            "fused_rollout", "pack_policy_weights", "pack_policy_weights_tc"]

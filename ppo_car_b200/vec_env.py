@@ -55,7 +55,7 @@ def _ptr(t):
 
 class VecCarEnv:
     def __init__(self, n_envs: int, track_path: str | None = None, device="cuda", reward_scaling: float = 1.0,
-                 float_flags: bool = False, with_info: bool = True):
+                 float_flags: bool = False, with_info: bool = True, _out: dict | None = None):
         if n_envs < 1:
             raise ValueError("n_envs must be >= 1")
         self._L = _lib.lib()                       # raises if the CUDA extension is missing
@@ -83,11 +83,15 @@ class VecCarEnv:
         self.vel = torch.zeros((n, 2), dtype=torch.float64, device=dev)
         self.ints = torch.zeros((n, 4), dtype=torch.int32, device=dev)
         fdt = torch.float32 if self.float_flags else torch.uint8
-        self._obs = torch.empty((n, OBS_DIM), dtype=torch.float32, device=dev)
-        self._rew = torch.empty((n,), dtype=torch.float32, device=dev)
-        self._term = torch.empty((n,), dtype=fdt, device=dev)
-        self._trunc = torch.empty((n,), dtype=fdt, device=dev)
-        self._info = torch.empty((n, 4), dtype=torch.int32, device=dev) if self.with_info else None
+        if _out is not None:                      # output rows owned by a MultiTrackVecEnv (contiguous slices)
+            self._obs, self._rew, self._term, self._trunc = _out["obs"], _out["rew"], _out["term"], _out["trunc"]
+            self._info = _out.get("info") if self.with_info else None
+        else:
+            self._obs = torch.empty((n, OBS_DIM), dtype=torch.float32, device=dev)
+            self._rew = torch.empty((n,), dtype=torch.float32, device=dev)
+            self._term = torch.empty((n,), dtype=fdt, device=dev)
+            self._trunc = torch.empty((n,), dtype=fdt, device=dev)
+            self._info = torch.empty((n, 4), dtype=torch.int32, device=dev) if self.with_info else None
         self._host = None                          # pinned staging buffers, created on first numpy call
         self._needs_reset = True
         self._set_track(track_path or builtin_track("track"))   # reference default: tracks/track.json
@@ -283,3 +287,62 @@ class VecCarEnv:
             self.close()
         except Exception:
             pass
+
+
+class MultiTrackVecEnv:
+    """Several tracks in one vector env: environments [lo_i, hi_i) run on track i.  Every group is
+    a VecCarEnv with its own handle (per-track tables) writing straight into its slice of the shared output
+    tensors, so ``step`` returns the same 5-tuple as VecCarEnv over all environments; the groups' kernels are
+    launched back to back on the caller's stream."""
+
+    def __init__(self, groups, device="cuda", reward_scaling: float = 1.0, float_flags: bool = False):
+        """groups: list of (track_path, n_envs)."""
+        if not groups:
+            raise ValueError("need at least one (track_path, n_envs) group")
+        self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = sum(int(n) for _, n in groups)
+        n, dev = self.num_envs, self.device
+        fdt = torch.float32 if float_flags else torch.uint8
+        self._obs = torch.empty((n, OBS_DIM), dtype=torch.float32, device=dev)
+        self._rew = torch.empty((n,), dtype=torch.float32, device=dev)
+        self._term = torch.empty((n,), dtype=fdt, device=dev)
+        self._trunc = torch.empty((n,), dtype=fdt, device=dev)
+        self._info = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        self.float_flags = bool(float_flags)
+        self.envs, self.ranges, lo = [], [], 0
+        for path, cnt in groups:
+            hi = lo + int(cnt)
+            out = dict(obs=self._obs[lo:hi], rew=self._rew[lo:hi], term=self._term[lo:hi], trunc=self._trunc[lo:hi],
+                       info=self._info[lo:hi])
+            self.envs.append(VecCarEnv(int(cnt), path, device=dev, reward_scaling=reward_scaling,
+                                       float_flags=float_flags, with_info=True, _out=out))
+            self.ranges.append((lo, hi))
+            lo = hi
+        self.single_observation_space = self.envs[0].single_observation_space
+        self.single_action_space = self.envs[0].single_action_space
+
+    def reset(self, seed=None, options=None):
+        for env in self.envs:
+            env.reset(seed=seed)
+        zeros = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        return self._obs, {"gates_passed": zeros, "time_passed": zeros.clone()}
+
+    def step(self, actions: torch.Tensor):
+        if not (isinstance(actions, torch.Tensor) and actions.is_cuda):
+            actions = torch.as_tensor(np.asarray(actions), device=self.device)
+        actions = actions.reshape(-1)
+        if actions.numel() != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} actions, got {actions.numel()}")
+        for env, (lo, hi) in zip(self.envs, self.ranges):
+            env._step_device(actions[lo:hi])
+        term = self._term if self.float_flags else self._term.view(torch.bool)
+        trunc = self._trunc if self.float_flags else self._trunc.view(torch.bool)
+        info = {"gates_passed": self._info[:, 0], "time_passed": self._info[:, 1], "next_gate_index": self._info[:, 2],
+                "events": self._info[:, 3]}
+        return self._obs, self._rew, term, trunc, info
+
+    def close(self):
+        for env in self.envs:
+            env.close()

@@ -77,3 +77,28 @@ def test_track_loader_matches_reference_construction(tracks_dir):
         assert a.start == tuple(b["start"]) and a.angle == b["angle"]
     with pytest.raises(FileNotFoundError):
         ppo_car_b200.load_track(os.path.join(tracks_dir, "nope.json"))
+
+
+def test_track_validation(tmp_path, tracks_dir):
+    import json
+
+    from ppo_car_b200.track import validate_track
+
+    for name in ("track", "big_track"):
+        assert validate_track(os.path.join(tracks_dir, name + ".json")) == []
+    raw = json.load(open(os.path.join(tracks_dir, "track.json")))
+
+    def variant(**changes):
+        d = dict(raw)
+        d.update(changes)
+        p = tmp_path / "v.json"
+        p.write_text(json.dumps(d))
+        return validate_track(str(p))
+
+    assert any("not closed" in m for m in variant(outer_track_points=raw["outer_track_points"][:-1]))
+    assert any("odd number" in m for m in variant(reward_gates=raw["reward_gates"][:-1]))
+    assert any("outside the outer" in m for m in variant(initial_position=[0.001, 0.001]))
+    assert any("inside the inner" in m for m in variant(initial_position=[0.5, 0.5]))
+    wall_y = raw["outer_track_points"][0][1]
+    assert any("closer than 10 px" in m or "outside" in m
+               for m in variant(initial_position=[raw["initial_position"][0], wall_y - 0.005]))

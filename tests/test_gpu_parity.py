@@ -369,3 +369,25 @@ def test_adversarial_poses_on_gpu(tracks_dir):
     assert_floats_close(obs.cpu().numpy()[alive][:, 6:], fobs_ref[alive][:, 6:], "ray distances at adversarial poses")
     counts = env.slow_path_counts()
     assert counts["line"] + counts["band"] > 500 and 0 < alive.sum() < n
+
+
+def test_multi_track_vector_env(tracks_dir):
+    """Two tracks in one vector env: each group's rows equal a single-track VecCarEnv stepped with the same actions."""
+    pa, pb = os.path.join(tracks_dir, "track.json"), os.path.join(tracks_dir, "big_track.json")
+    multi = ppo_car_b200.MultiTrackVecEnv([(pa, 300), (pb, 500)], reward_scaling=0.1)
+    ea, eb = ppo_car_b200.VecCarEnv(300, pa, reward_scaling=0.1), ppo_car_b200.VecCarEnv(500, pb, reward_scaling=0.1)
+    obs, _ = multi.reset()
+    oa, _ = ea.reset()
+    ob, _ = eb.reset()
+    assert torch.equal(obs[:300], oa) and torch.equal(obs[300:], ob) and not torch.equal(obs[0], obs[-1])
+    g = torch.Generator(device="cuda").manual_seed(6)
+    for _ in range(120):
+        a = torch.randint(0, 9, (800,), generator=g, device="cuda")
+        o, r, te, tr, info = multi.step(a)
+        o1, r1, te1, tr1, i1 = ea.step(a[:300])
+        o2, r2, te2, tr2, i2 = eb.step(a[300:])
+        assert torch.equal(o[:300], o1) and torch.equal(o[300:], o2)
+        assert torch.equal(r[:300], r1) and torch.equal(r[300:], r2)
+        assert torch.equal(te[:300], te1) and torch.equal(te[300:], te2)
+        assert torch.equal(info["gates_passed"][300:], i2["gates_passed"])
+    multi.close()

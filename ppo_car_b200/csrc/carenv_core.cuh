@@ -69,9 +69,10 @@ struct TrackParams {
     float tiny_d;       // distances below this are re-evaluated (sign of u uncertain)
     float gate_band;    // gate margin band, in units of the gate length
     float tiny_un;      // |cross(e, A')| below this: every line is re-evaluated
-    int unroll;         // largest U in {4, 2, 1} such that n_seg and every polyline start are multiples of U;
+    int unroll;         // first U of {6, 4, 2, 1} such that n_seg and every polyline start are multiples of U;
                         // 0 for tracks with more than kMaxSeg segments (geometry from Tables::segf/segd)
-    int pad2[2];
+    int unroll4;        // same, restricted to {4, 2, 1} (the fused rollout kernels)
+    int pad2;
     double start_x, start_y;
     float reset_obs[kObsDim];
     float pad1[2];

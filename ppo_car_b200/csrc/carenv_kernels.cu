@@ -638,9 +638,10 @@ int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel,
                    double reward_scale, float *obs_out, float *reward_out, void *term_out, void *trunc_out,
                    int32_t *info_out, cudaStream_t stream) {
     int U = h->force_generic ? 1 : h->host.P.unroll;
-    if (h->max_unroll > 0 && U > h->max_unroll) U = h->max_unroll;
+    if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
     if (h->host.P.n_seg > kMaxSeg) U = 0;                   // geometry from shared memory
 #define ARGS h, n_envs, n_steps, pos, vel, ints, actions, reward_scale, obs_out, reward_out, term_out, trunc_out, info_out, stream
+    if (U == 6) return launch_rollout_t<ActT, FlagT, 6>(ARGS);
     if (U == 4) return launch_rollout_t<ActT, FlagT, 4>(ARGS);
     if (U == 2) return launch_rollout_t<ActT, FlagT, 2>(ARGS);
     if (U == 0) return launch_rollout_t<ActT, FlagT, 0>(ARGS);
@@ -810,7 +811,7 @@ int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs,
     const size_t smem = (size_t)table_bytes + sizeof(float) * kPolicyFloats;
     const int grid = (n_envs + kPolicyBlock - 1) / kPolicyBlock;
     int U = h->force_generic ? 1 : h->host.P.unroll;
-    if (h->max_unroll > 0 && U > h->max_unroll) U = h->max_unroll;
+    if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
     auto launch = [&](auto kern) -> int {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kPolicyBlock, smem, static_cast<cudaStream_t>(stream)>>>(
@@ -862,7 +863,7 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
     if (smem > 227 * 1024) return fail(CARENV_E_TRACK, "track tables too large for the tensor-core rollout kernel");
     const int grid = (n_envs + kTcTiles * 128 - 1) / (kTcTiles * 128);
     int U = h->force_generic ? 1 : h->host.P.unroll;
-    if (h->max_unroll > 0 && U > h->max_unroll) U = h->max_unroll;
+    if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
     auto launch = [&](auto kern) -> int {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kTcThreads, smem, static_cast<cudaStream_t>(stream)>>>(

@@ -30,6 +30,7 @@ extern "C" int emul_rollout(const double *walls, int n_walls, const double *gate
             StepResult o;
             const int U = H.P.n_seg > kMaxSeg ? 0 : (unrolled ? H.P.unroll : 1);
             if (U == 0) env_step<0>(s, actions[k], reward_scale, H.P, Tb, o, stats);
+            else if (U == 6) env_step<6>(s, actions[k], reward_scale, H.P, Tb, o, stats);
             else if (U == 4) env_step<4>(s, actions[k], reward_scale, H.P, Tb, o, stats);
             else if (U == 2) env_step<2>(s, actions[k], reward_scale, H.P, Tb, o, stats);
             else env_step<1>(s, actions[k], reward_scale, H.P, Tb, o, stats);

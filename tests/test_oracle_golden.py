@@ -94,3 +94,24 @@ def test_gae_port_bit_exact(golden_dir, tag):
                         g[f"{tag}_last_val"], g[f"{tag}_last_term"], g[f"{tag}_last_trunc"])
     assert np.array_equal(adv, g[f"{tag}_adv"])
     assert np.array_equal(ret, g[f"{tag}_ret"])
+
+
+def test_port_against_live_reference_when_available(tracks_dir):
+    """In the build container the unmodified reference is mounted: replay fresh random actions through it and
+    through the port (bit-exact).  Skipped on the GPU box, where /root/reference does not exist."""
+    from oracle.ref_import import RefVecEnv, reference_available, track_path
+
+    if not reference_available():
+        pytest.skip("reference tree not mounted")
+    rng = np.random.default_rng(2024)
+    for name in TRACK_NAMES:
+        acts = rng.choice(9, size=(150, 3), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04])
+        ref, port = RefVecEnv(3, track_path(name + ".json")), PortVecEnv(3, os.path.join(tracks_dir, name + ".json"))
+        assert np.array_equal(ref.reset(), port.reset())
+        for t in range(acts.shape[0]):
+            o1, r1, te1, tr1, i1 = ref.step(acts[t])
+            o2, r2, te2, tr2, i2 = port.step(acts[t])
+            assert np.array_equal(o1, o2) and np.array_equal(r1, r2), (name, t)
+            assert np.array_equal(te1, te2) and np.array_equal(tr1, tr2)
+            assert np.array_equal(i1["gates_passed"], i2["gates_passed"])
+            assert np.array_equal(i1["next_gate_index"], i2["next_gate_index"])

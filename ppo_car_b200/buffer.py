@@ -59,6 +59,7 @@ class Buffer:
         self.logprob_buf = z(size, num_envs)
         self.gamma, self.gae_lambda = gamma, gae_lambda
         self.ptr = 0
+        self._adv = self._ret = None          # allocated on first use and reused (static addresses: CUDA graphs)
 
     def store(self, obs, act, rew, val, term, trunc, logprob):
         """Store one step; first dimension is the step, second the environment (lib/buffer.py:22-34)."""
@@ -75,9 +76,12 @@ class Buffer:
     def calculate_advantages(self, last_vals, last_terminateds, last_truncateds):
         """GAE over the full buffer; returns (adv_buf, ret_buf) (lib/buffer.py:36-64)."""
         assert self.ptr == self.capacity, "Buffer not full"
+        if self._adv is None:
+            self._adv, self._ret = torch.empty_like(self.rew_buf), torch.empty_like(self.rew_buf)
         with torch.no_grad():
             return gae_reverse_scan(self.rew_buf, self.val_buf, self.term_buf, self.trunc_buf, last_vals,
-                                    last_terminateds, last_truncateds, self.gamma, self.gae_lambda)
+                                    last_terminateds, last_truncateds, self.gamma, self.gae_lambda,
+                                    adv_out=self._adv, ret_out=self._ret)
 
     def get(self):
         """obs_buf, act_buf, val_buf, logprob_buf; rewinds the write pointer (lib/buffer.py:66-73)."""

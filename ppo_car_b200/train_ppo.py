@@ -89,6 +89,9 @@ def parse_args(argv=None):
     p.add_argument("--fused-rollout", action="store_true",
                    help="run the whole rollout (policy forward, sampling, env step, buffer rows) in ONE kernel launch "
                         "per epoch (carenv_policy_rollout); needs the reference network shape")
+    p.add_argument("--graph-update", action="store_true",
+                   help="capture one minibatch update (sampling, forward, backward, clip, Adam) in a CUDA graph and "
+                        "replay it train_iters x minibatches times per epoch (single-process runs only)")
     p.add_argument("--cuda-graph", action="store_true",
                    help="capture the whole n_steps rollout (policy forward, sampling, env step, buffer rows) in one "
                         "CUDA graph and replay it every epoch: removes the per-step launch overhead at small n_envs")
@@ -113,8 +116,14 @@ def train(args) -> list[dict]:
     envs = VecCarEnv(n, track, device=dev, reward_scaling=args.reward_scaling, float_flags=True, with_info=False)
     obs_dim = envs.single_observation_space.shape
     agent = ActorCritic(obs_dim[0], envs.single_action_space.n).to(dev)
-    opt = torch.optim.Adam(agent.parameters(), lr=args.learning_rate, eps=1e-5)
-    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=args.learning_rate_decay)
+    graph_update = bool(args.graph_update) and world == 1
+    if graph_update:                                        # capturable Adam with the learning rate in a tensor
+        opt = torch.optim.Adam(agent.parameters(), lr=torch.tensor(args.learning_rate, device=dev), eps=1e-5,
+                               capturable=True)
+        sched = None
+    else:
+        opt = torch.optim.Adam(agent.parameters(), lr=args.learning_rate, eps=1e-5)
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=args.learning_rate_decay)
     params = [p for p in agent.parameters()]
     buf = Buffer(obs_dim, T, n, dev, args.gamma, args.gae_lambda)
     torch.manual_seed(args.seed * 1000 + rank + 1)     # different sampling noise per shard
@@ -189,11 +198,14 @@ def train(args) -> list[dict]:
         adv_f, ret_f = adv.view(-1), ret.view(-1)
 
         # ---- update (train.py:223-261)
-        sums = torch.zeros(4, device=dev)
-        for _ in range(args.train_iters):
-            idx_all = torch.randint(0, T * n, (n_mb, args.batch_size), device=dev)
-            for m in range(n_mb):
-                idx = idx_all[m]
+        if epoch == 1:
+            sums = torch.zeros(4, device=dev)
+            idx_static = torch.zeros(args.batch_size, dtype=torch.int64, device=dev)
+
+            def update_step():
+                """One minibatch: draw indices, clipped-surrogate loss, backward, (all-reduce), clip, Adam."""
+                torch.randint(0, T * n, (args.batch_size,), device=dev, out=idx_static)
+                idx = idx_static
                 _, new_logp, ent, new_val = agent.act(obs_f[idx], act_f[idx])
                 ratio = torch.exp(new_logp - logp_f[idx])
                 a = adv_f[idx]
@@ -214,13 +226,35 @@ def train(args) -> list[dict]:
                         off += p.numel()
                 nn.utils.clip_grad_norm_(params, args.max_grad_norm)
                 opt.step()
-                sums += torch.stack([pol.detach(), vl.detach(), e.detach(), loss.detach()])
-        sched.step()
+                sums.add_(torch.stack([pol.detach(), vl.detach(), e.detach(), loss.detach()]))
+
+            update_graph = None
+            if graph_update:                                # obs_f, act_f, ... are views of the static buffer tensors
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(3):                      # warm-up (also creates Adam's state) counts as 3 real steps
+                        update_step()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                update_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(update_graph):
+                    update_step()
+                sums.zero_()
+        sums.zero_()
+        for _ in range(args.train_iters * n_mb):
+            if update_graph is not None:
+                update_graph.replay()
+            else:
+                update_step()
+        if sched is not None:
+            sched.step()
+        else:
+            opt.param_groups[0]["lr"].mul_(args.learning_rate_decay)
 
         s = (sums / args.train_iters).tolist()
         rec = {"epoch": epoch, "global_step": global_step, "avg_reward": rew_sum / steps / args.reward_scaling,
                "episodes": episodes, "policy_loss": s[0], "value_loss": s[1], "entropy": s[2], "total_loss": s[3],
-               "lr": opt.param_groups[0]["lr"], "sps": global_step / (time.time() - t_start),
+               "lr": float(opt.param_groups[0]["lr"]), "sps": global_step / (time.time() - t_start),
                "wall_s": time.time() - t_start}
         history.append(rec)
         if rank == 0:

@@ -47,3 +47,13 @@ def test_cuda_graph_rollout_trains():
     assert all(math.isfinite(h["total_loss"]) for h in hist)
     assert hist[-1]["avg_reward"] > hist[0]["avg_reward"] + 0.02
     assert hist[0]["episodes"] > 0
+
+
+@pytest.mark.gpu
+def test_graph_update_trains():
+    args = parse_args(["--track", "big_track", "--n-envs", "64", "--n-epochs", "12", "--n-steps", "256",
+                       "--fused-rollout", "--graph-update"])
+    hist = train(args)
+    assert all(math.isfinite(h["total_loss"]) for h in hist)
+    assert hist[-1]["avg_reward"] > hist[0]["avg_reward"] + 0.03
+    assert abs(hist[-1]["lr"] - 3e-4 * 0.99 ** 12) < 1e-9

@@ -10,8 +10,11 @@ environments in total, i.i.d. uniform random actions, sharded over the N ranks b
 ranges with no data-path collective (strong scaling: the total is fixed).  One timed "step" is
 `launches` back-to-back `carenv_rollout` launches per rank, each advancing every local environment
 by `chunk` CarEnv steps and writing the observation, reward and both flags of every one of them to
-HBM (default 8 x 32 = 256 env steps per environment per bench step, so that K = 20 steps keep the
-GPU busy for about half a second and the clock samples are taken under load).
+HBM (default 1 x 256 env steps per environment per bench step, so that K = 20 steps keep the GPU busy
+for about half a second and the clock samples are taken under load; a launch has a start-up transient
+of about 25 us per wave of resident blocks — all warps begin in the same phase of the step and
+compete for the FP64/XU pipes until they drift apart, benchmarks/sweep_launch.py — so short launches
+such as 8 x 32 measure 2-18 % less, depending on the shard size).
 
   value     env-steps/s with actions already resident in HBM (device timed, CUDA events, max over ranks)
   e2e       env-steps/s through the reference-facing API VecCarEnv.step(numpy actions) -> numpy
@@ -396,8 +399,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=TOTAL_ENVS, help="total environments over all GPUs")
-    ap.add_argument("--chunk", type=int, default=32, help="env steps per rollout launch")
-    ap.add_argument("--launches", type=int, default=8, help="rollout launches per timed bench step")
+    ap.add_argument("--chunk", type=int, default=256, help="env steps per rollout launch")
+    ap.add_argument("--launches", type=int, default=1, help="rollout launches per timed bench step")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -50,6 +50,8 @@ struct Handle {
     size_t smem_bytes;
     int force_generic;        // test hook: run the generic (not unrolled) kernel
     int max_unroll;           // tuning hook: cap the segment-loop unrolling (0 = no cap)
+    int block;                // tuning hook: threads per block of k_rollout (0 = chosen per launch, see rollout_block)
+    int smem_pad;             // tuning hook: extra dynamic shared memory per block (limits resident blocks per SM)
 };
 
 struct DeviceGuard {
@@ -620,10 +622,12 @@ int launch_rollout_t(Handle *h, int n_envs, int n_steps, double *pos, double *ve
                    double reward_scale, float *obs_out, float *reward_out, void *term_out, void *trunc_out,
                    int32_t *info_out, cudaStream_t stream) {
     auto kern = k_rollout<ActT, FlagT, U>;
-    if (h->smem_bytes > 48 * 1024)
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    const int grid = (n_envs + kBlock - 1) / kBlock;
-    kern<<<grid, kBlock, h->smem_bytes, stream>>>(
+    const int block = h->block > 0 ? h->block : kBlock;
+    const size_t smem = h->smem_bytes + (size_t)h->smem_pad;
+    if (smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (n_envs + block - 1) / block;
+    kern<<<grid, block, smem, stream>>>(
         h->host.P, h->dev, n_envs, n_steps, reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel),
         reinterpret_cast<int4 *>(ints), static_cast<const ActT *>(actions), reward_scale, obs_out, reward_out,
         static_cast<FlagT *>(term_out), static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out),
@@ -696,7 +700,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -884,6 +888,14 @@ int carenv_set_option(void *handle, const char *name, int value) {
     if (!h || !name) return fail(CARENV_E_INVAL, "null argument");
     if (std::string(name) == "force_generic") { h->force_generic = value ? 1 : 0; return 0; }
     if (std::string(name) == "max_unroll") { h->max_unroll = value; return 0; }
+    if (std::string(name) == "block") {
+        if (value < 0 || value > kBlock || value % 32) return fail(CARENV_E_INVAL, "block must be 0, 32, 64, 96 or 128");
+        h->block = value; return 0;
+    }
+    if (std::string(name) == "smem_pad") {
+        if (value < 0 || value > 100 * 1024) return fail(CARENV_E_INVAL, "smem_pad must be in 0..102400");
+        h->smem_pad = value; return 0;
+    }
     return fail(CARENV_E_INVAL, std::string("unknown option ") + name);
 }
 

@@ -91,7 +91,7 @@ def parse_args(argv=None):
                         "per epoch (carenv_policy_rollout); needs the reference network shape")
     p.add_argument("--graph-update", action="store_true",
                    help="capture one minibatch update (sampling, forward, backward, clip, Adam) in a CUDA graph and "
-                        "replay it train_iters x minibatches times per epoch (single-process runs only)")
+                        "replay it train_iters x minibatches times per epoch (the NCCL gradient all-reduce is captured too)")
     p.add_argument("--cuda-graph", action="store_true",
                    help="capture the whole n_steps rollout (policy forward, sampling, env step, buffer rows) in one "
                         "CUDA graph and replay it every epoch: removes the per-step launch overhead at small n_envs")
@@ -116,7 +116,7 @@ def train(args) -> list[dict]:
     envs = VecCarEnv(n, track, device=dev, reward_scaling=args.reward_scaling, float_flags=True, with_info=False)
     obs_dim = envs.single_observation_space.shape
     agent = ActorCritic(obs_dim[0], envs.single_action_space.n).to(dev)
-    graph_update = bool(args.graph_update) and world == 1
+    graph_update = bool(args.graph_update)                 # with world > 1 the NCCL all-reduce is captured too
     if graph_update:                                        # capturable Adam with the learning rate in a tensor
         opt = torch.optim.Adam(agent.parameters(), lr=torch.tensor(args.learning_rate, device=dev), eps=1e-5,
                                capturable=True)

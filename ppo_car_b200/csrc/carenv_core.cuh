@@ -52,13 +52,23 @@ struct F2 { float x, y; };
 struct D2 { double x, y; };
 
 // One wall segment A->B in float32 (endpoints rounded from float64; they only feed sign tests).
-struct SegF {
-    float ahx, ahy, bhx, bhy;
+struct alignas(16) SegF {
+    float bhx, bhy;        // first 16 bytes = what every segment needs: one 128-bit uniform load
+    float ney, ey;         // (-ey, ey) adjacent and 8-byte aligned: one packed operand of the den computation
     float ex;              // B - A rounded from float64
-    float ney, ey;         // (-ey, ey) adjacent: one packed operand of the den computation
     int chain_start;       // 1: A is not the previous segment's B
+    float ahx, ahy;        // only read at a polyline start
 };
-struct SegD { double K, ex, ey; };   // K = cross(e, A):  cross(e, A - pos) = K - (ex*py - ey*px)
+struct SegHead { float bhx, bhy, ney, ey; };
+#if defined(__CUDA_ARCH__)
+CE_HD SegHead seg_head(const SegF &f) {
+    const float4 v = *reinterpret_cast<const float4 *>(&f);
+    return SegHead{v.x, v.y, v.z, v.w};
+}
+#else
+CE_HD SegHead seg_head(const SegF &f) { return SegHead{f.bhx, f.bhy, f.ney, f.ey}; }
+#endif
+struct SegD { double K, ex, ey; };   // K = cross(e, A):  cross(e, A - pos) = K - (ex*py - ey*px)   // K = cross(e, A):  cross(e, A - pos) = K - (ex*py - ey*px)
 
 struct GateRec { double x1, y1, x2, y2; float ex, ey, len, pad; };
 
@@ -344,8 +354,9 @@ CE_HD void wall_chain_start2(WallAcc2 &w, const SegF &f) {
 CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1, const SegD &g1, double px,
                      double py) {
     P2 QB0[3], QB1[3];
-    wall_point2(w, f0.bhx, f0.bhy, QB0);
-    wall_point2(w, f1.bhx, f1.bhy, QB1);
+    const SegHead h0 = seg_head(f0), h1 = seg_head(f1);     // bhx, bhy, -ey, ey: one 128-bit uniform load each
+    wall_point2(w, h0.bhx, h0.bhy, QB0);
+    wall_point2(w, h1.bhx, h1.bhy, QB1);
     const float un0 = (float)dfma(g0.ey, px, dfma(-g0.ex, py, g0.K));
     const float un1 = (float)dfma(g1.ey, px, dfma(-g1.ex, py, g1.K));
     const float inv0 = frcp(un0), inv1 = frcp(un1);
@@ -353,8 +364,8 @@ CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
         const P2 SW = p2(w.S[l].y, w.S[l].x);
-        const P2 R0 = pmul(pfma(p2(f0.ex, f0.ex), w.S[l], pmul(p2(f0.ney, f0.ey), SW)), p2(inv0, inv0));
-        const P2 R1 = pmul(pfma(p2(f1.ex, f1.ex), w.S[l], pmul(p2(f1.ney, f1.ey), SW)), p2(inv1, inv1));
+        const P2 R0 = pmul(pfma(p2(f0.ex, f0.ex), w.S[l], pmul(p2(h0.ney, h0.ey), SW)), p2(inv0, inv0));
+        const P2 R1 = pmul(pfma(p2(f1.ex, f1.ex), w.S[l], pmul(p2(h1.ney, h1.ey), SW)), p2(inv1, inv1));
         const P2 W0 = pmul(w.QA[l], QB0[l]), W1 = pmul(QB0[l], QB1[l]);
         const P2 H0 = pmul(R0, p2(neg_mask(W0.x), neg_mask(W0.y)));
         const P2 H1 = pmul(R1, p2(neg_mask(W1.x), neg_mask(W1.y)));

@@ -99,6 +99,7 @@ __device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, int
     const SegF *s_segf = nullptr;
     const SegD *s_segd = nullptr;
     if (n_seg > kMaxSeg) {                                  // big track: the segment records live in shared memory too
+        static_assert(sizeof(SegF) == 32 && sizeof(SegD) == 24, "staging below copies 4 / 3 doubles per record");
         double *d4 = s_walls + 4 * n_seg, *d5 = d4 + 4 * n_seg;            // SegF = 4 doubles, SegD = 3 doubles
         const double *g4 = reinterpret_cast<const double *>(G.segf), *g5 = reinterpret_cast<const double *>(G.segd);
         for (int i = threadIdx.x; i < 4 * n_seg; i += blockDim.x) d4[i] = g4[i];

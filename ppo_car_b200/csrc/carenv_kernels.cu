@@ -52,6 +52,7 @@ struct Handle {
     int max_unroll;           // tuning hook: cap the segment-loop unrolling (0 = no cap)
     int block;                // tuning hook: threads per block of k_rollout (0 = chosen per launch, see rollout_block)
     int smem_pad;             // tuning hook: extra dynamic shared memory per block (limits resident blocks per SM)
+    int tc_tiles;             // tuning hook: 128-env groups per CTA of k_policy_rollout_tc (0 = chosen per launch)
 };
 
 struct DeviceGuard {
@@ -293,18 +294,16 @@ k_policy_rollout(const __grid_constant__ TrackParams P, const Tables G, const fl
 // accuracy) — into tensor memory, and after the commit barrier every thread reads ITS row of pre-activations
 // back with tcgen05.ld, applies ReLU and the small second layer (FFMA2) and goes on to sampling and the env step.
 // TMEM: 512 columns = kTcTiles x kTcCols; the 256 hidden units of a net are produced in 256 / kTcCols rounds.
-constexpr int kTcTiles = 4;                                  // 128-env groups per CTA (512 threads)
-constexpr int kTcCols = 512 / kTcTiles;                      // accumulator columns per group and round (128)
-constexpr int kTcRounds = kHidden / kTcCols;                 // rounds per net (2)
+// TILES = 128-env groups per CTA: 4 (512 environment threads, TMEM 4 x 128 columns, two rounds per net) for large
+// shards, 2 (256 threads, 2 x 256 columns, one round per net) for shards that would otherwise leave SMs empty.
 constexpr int kTcBFloats = tc::kTileN * tc::kK;              // 6,144 floats per B operand
 constexpr int kTcW2Off = 4 * kTcBFloats;                     // [actor hi | actor lo | critic hi | critic lo]
 constexpr int kTcW2cOff = kTcW2Off + kHidden * 10;           // W2 actor as [j][5] pairs, then w2c[j]
 constexpr int kTcTailOff = kTcW2cOff + kHidden;              // b2[0..9], b2c, pad
 constexpr int kTcWeightFloats = kTcTailOff + 12;             // 27,404 floats
-constexpr int kTcThreads = kTcTiles * 128 + 32;            // four 128-env groups + one MMA-issuing warp
 
-template <int U>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int U, int TILES>
+__global__ void __launch_bounds__(TILES * 128 + 32, 1)
 k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const float *__restrict__ weights,
                     int n_envs, int n_steps, int env_offset, unsigned long long seed, unsigned long long step0,
                     double2 *__restrict__ pos, double2 *__restrict__ vel, int4 *__restrict__ ints,
@@ -313,6 +312,10 @@ k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const
                     float *__restrict__ rew_buf, float *__restrict__ val_buf, float *__restrict__ term_buf,
                     float *__restrict__ trunc_buf, float *__restrict__ logp_buf, float *__restrict__ last_val,
                     float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes) {
+    constexpr int kTcTiles = TILES;                          // 128-env groups per CTA (+ one MMA-issuing warp)
+    constexpr int kTcCols = 512 / TILES;                     // accumulator columns per group and round
+    constexpr int kTcRounds = kHidden / kTcCols;             // rounds per net
+    static_assert(TILES == 2 || TILES == 4, "TMEM: 512 columns = TILES x (256 or 128)");
     extern __shared__ __align__(16) unsigned char smem[];
     // [tables | pad to a 128-byte boundary | weights | A tiles (hi, lo per group)]
     const int w_off = (int)((tc::smem_u32(smem) + (uint32_t)table_bytes + 127u) / 128u * 128u - tc::smem_u32(smem));
@@ -701,7 +704,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -863,15 +866,20 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
     DeviceGuard guard(h->device);
     if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
     const int table_bytes = (int)h->smem_bytes;
+    // groups per CTA: 2 while 4 would leave SMs without a CTA (one CTA per SM: the weights take 110 KB)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    int tiles = (n_envs + 511) / 512 >= sms ? 4 : 2;
+    if (h->tc_tiles == 2 || h->tc_tiles == 4) tiles = h->tc_tiles;
     const size_t smem = (size_t)table_bytes + 128 + (size_t)((kTcWeightFloats * 4 + 127) / 128 * 128) +
-                        (size_t)kTcTiles * 2 * tc::kABytes;
+                        (size_t)tiles * 2 * tc::kABytes;
     if (smem > 227 * 1024) return fail(CARENV_E_TRACK, "track tables too large for the tensor-core rollout kernel");
-    const int grid = (n_envs + kTcTiles * 128 - 1) / (kTcTiles * 128);
+    const int grid = (n_envs + tiles * 128 - 1) / (tiles * 128);
     int U = h->force_generic ? 1 : h->host.P.unroll;
     if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
     auto launch = [&](auto kern) -> int {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kTcThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        kern<<<grid, tiles * 128 + 32, smem, static_cast<cudaStream_t>(stream)>>>(
             h->host.P, h->dev, packed_weights, n_envs, n_steps, env_offset, seed, step0,
             reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints), cur_obs,
             cur_term, cur_trunc, reward_scale, obs_buf, act_buf, rew_buf, val_buf, term_buf, trunc_buf, logp_buf,
@@ -879,9 +887,14 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
         CU(cudaGetLastError());
         return 0;
     };
-    if (U == 4) return launch(k_policy_rollout_tc<4>);
-    if (U == 2) return launch(k_policy_rollout_tc<2>);
-    return launch(k_policy_rollout_tc<1>);
+    if (tiles == 4) {
+        if (U == 4) return launch(k_policy_rollout_tc<4, 4>);
+        if (U == 2) return launch(k_policy_rollout_tc<2, 4>);
+        return launch(k_policy_rollout_tc<1, 4>);
+    }
+    if (U == 4) return launch(k_policy_rollout_tc<4, 2>);
+    if (U == 2) return launch(k_policy_rollout_tc<2, 2>);
+    return launch(k_policy_rollout_tc<1, 2>);
 }
 
 int carenv_set_option(void *handle, const char *name, int value) {
@@ -892,6 +905,10 @@ int carenv_set_option(void *handle, const char *name, int value) {
     if (std::string(name) == "block") {
         if (value < 0 || value > kBlock || value % 32) return fail(CARENV_E_INVAL, "block must be 0, 32, 64, 96 or 128");
         h->block = value; return 0;
+    }
+    if (std::string(name) == "tc_tiles") {
+        if (value != 0 && value != 2 && value != 4) return fail(CARENV_E_INVAL, "tc_tiles must be 0, 2 or 4");
+        h->tc_tiles = value; return 0;
     }
     if (std::string(name) == "smem_pad") {
         if (value < 0 || value > 100 * 1024) return fail(CARENV_E_INVAL, "smem_pad must be in 0..102400");

@@ -152,9 +152,9 @@ def train(args) -> list[dict]:
     if args.fused_rollout:
         from .policy import fused_rollout, pack_policy_weights, pack_policy_weights_tc
 
-        # tensor-core kernel (512-thread CTAs) once there are enough environments to fill the SMs,
-        # CUDA-core kernel (128-thread CTAs, lower latency) for small shards
-        pack_policy = pack_policy_weights_tc if n >= 65536 else pack_policy_weights
+        # tensor-core kernel (256- or 512-environment CTAs, chosen by the library from the shard size) from 4,096
+        # environments per shard (benchmarks/fused_tiles.py), CUDA-core kernel (128-thread CTAs) below
+        pack_policy = pack_policy_weights_tc if n >= 4096 else pack_policy_weights
         packed = pack_policy(agent.actor, agent.critic)
         last_val = torch.empty(n, device=dev)
 

@@ -28,8 +28,10 @@ def test_pack_layout_matches_header_constants():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,tensor_cores", [(24, False), (1000, False), (24, True), (1000, True), (2049, True)])
+@pytest.mark.parametrize("n,tensor_cores", [(24, False), (1000, False), (24, 2), (1000, 2), (1000, 4), (2049, 4),
+                                            (1300, 2)])
 def test_fused_rollout_matches_torch_policy_and_env_kernel(tracks_dir, n, tensor_cores):
+    """tensor_cores: False = CUDA-core kernel, 2 / 4 = tensor-core kernel with that many 128-env groups per CTA."""
     dev = torch.device("cuda")
     path = os.path.join(tracks_dir, "big_track.json")
     T = 300
@@ -45,6 +47,8 @@ def test_fused_rollout_matches_torch_policy_and_env_kernel(tracks_dir, n, tensor
     last_val, u = torch.empty(n, device=dev), torch.empty((T, n), device=dev)
     pack = ppo_car_b200.pack_policy_weights_tc if tensor_cores else ppo_car_b200.pack_policy_weights
     packed = pack(net.actor, net.critic)
+    if tensor_cores:
+        env.set_option("tc_tiles", int(tensor_cores))
     ppo_car_b200.fused_rollout(env, packed, buf, cur_obs, cur_term, cur_trunc, seed=11, step0=5, last_val=last_val, u_dbg=u)
     torch.cuda.synchronize()
     assert buf.ptr == T

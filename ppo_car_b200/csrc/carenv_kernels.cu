@@ -818,7 +818,7 @@ int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs,
     const int table_bytes = (int)((h->smem_bytes + 15) / 16 * 16);
     const size_t smem = (size_t)table_bytes + sizeof(float) * kPolicyFloats;
     const int grid = (n_envs + kPolicyBlock - 1) / kPolicyBlock;
-    int U = h->force_generic ? 1 : h->host.P.unroll;
+    int U = h->force_generic ? 1 : h->host.P.unroll4;   // the fused kernels are instantiated for 4, 2, 1
     if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
     auto launch = [&](auto kern) -> int {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -875,7 +875,7 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
                         (size_t)tiles * 2 * tc::kABytes;
     if (smem > 227 * 1024) return fail(CARENV_E_TRACK, "track tables too large for the tensor-core rollout kernel");
     const int grid = (n_envs + tiles * 128 - 1) / (tiles * 128);
-    int U = h->force_generic ? 1 : h->host.P.unroll;
+    int U = h->force_generic ? 1 : h->host.P.unroll4;
     if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
     auto launch = [&](auto kern) -> int {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -91,6 +91,18 @@ int carenv_rollout(void *handle, int n_envs, int n_steps, double *pos, double *v
                    const void *actions, int action_dtype, double reward_scale, float *obs_out, float *reward_out,
                    void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream);
 
+/* Compact rollout storage (the reference stores obs [T][N][18] float32, lib/buffer.py:12).
+ * carenv_rollout_poses is carenv_rollout with a 32-byte pose record per env-step instead of the 72-byte
+ * observation: { double x, y; float obs2, obs3; int32 heading_index; int32 reset } — `reset` = 1 where the
+ * episode ended in that step (the row's observation is the reset observation).
+ * carenv_observe recomputes observations from n records (records poses[index[i]] if index is not NULL, else
+ * poses[i]) into obs_out [n][18]; the result is bit-identical to what carenv_rollout would have written. */
+#define CARENV_POSE_BYTES 32
+int carenv_rollout_poses(void *handle, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints,
+                         const void *actions, int action_dtype, double reward_scale, void *pose_out, float *reward_out,
+                         void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream);
+int carenv_observe(void *handle, long long n, const void *poses, const long long *index, float *obs_out, void *stream);
+
 /* Tuning / test options.  "force_generic" = 1 runs the generic segment loop even for tracks that have
  * a fully unrolled kernel instantiation (the two produce identical results). */
 int carenv_set_option(void *handle, const char *name, int value);

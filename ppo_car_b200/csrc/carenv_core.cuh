@@ -118,6 +118,14 @@ struct StepResult {
     int gate_hit, lap;
 };
 
+// Compact rollout row: what is needed to recompute the 72-byte observation bit for bit.
+struct alignas(16) PoseRec {
+    double px, py;      // position after the step (float64: the ray casting starts from it)
+    float vx10, vy10;   // obs[2], obs[3] as the step computed them
+    int k;              // heading index
+    int reset;          // 1: the row's observation is the reset observation (episode ended in this step)
+};
+
 // slow-path counters (optional)
 enum { kStatLine = 0, kStatBand = 1, kStatGate = 2, kStatTiny = 3, kNumStats = 4 };
 
@@ -486,6 +494,19 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
     return destroyed;
 }
 
+// ---- observation of a live pose (lib/car_env.py:569-597): normalised position, velocity, heading, rays ------
+CE_HD void pose_observation(const EnvState &s, float vx10, float vy10, const float dist[kNumRays], const Tables &T,
+                            float obs[kObsDim]) {
+    const F2 d = T.trig32[s.k];
+    obs[0] = (float)dmul(s.px, 1.0 / 1280.0);
+    obs[1] = (float)dmul(s.py, 1.0 / 720.0);
+    obs[2] = vx10;
+    obs[3] = vy10;
+    obs[4] = d.x; obs[5] = d.y;
+#pragma unroll
+    for (int i = 0; i < kNumRays; ++i) obs[6 + i] = fmul(dist[i], 1.0e-3f);
+}
+
 // ---- one CarEnv.step with same-step autoreset --------------------------------------------------
 template <int U>
 CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackParams &P, const Tables &T,
@@ -523,14 +544,7 @@ CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackPar
 #pragma unroll
         for (int i = 0; i < kObsDim; ++i) o.obs[i] = P.reset_obs[i];
     } else {
-        const F2 d = T.trig32[s.k];
-        o.obs[0] = (float)dmul(s.px, 1.0 / 1280.0);
-        o.obs[1] = (float)dmul(s.py, 1.0 / 720.0);
-        o.obs[2] = (float)dmul(s.vx, 0.1);
-        o.obs[3] = (float)dmul(s.vy, 0.1);
-        o.obs[4] = d.x; o.obs[5] = d.y;
-#pragma unroll
-        for (int i = 0; i < kNumRays; ++i) o.obs[6 + i] = fmul(dist[i], 1.0e-3f);
+        pose_observation(s, (float)dmul(s.vx, 0.1), (float)dmul(s.vy, 0.1), dist, T, o.obs);
     }
 }
 

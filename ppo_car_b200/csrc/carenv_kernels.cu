@@ -112,6 +112,46 @@ __device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, int
     return Tables{s_trig32, s_trig64, s_acc64, s_gates, s_walls, s_segf, s_segd};
 }
 
+// What k_rollout writes per env-step besides reward and flags (rollout storage format).
+enum { kObsNone = 0, kObsFull = 1, kObsPose = 2 };
+
+__device__ __forceinline__ void store_pose(PoseRec *dst, const EnvState &s, const StepResult &o) {
+    const int reset = o.terminated | o.truncated;            // the observation of this row is the reset observation
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+    d2[0] = make_double2(s.px, s.py);
+    reinterpret_cast<float4 *>(dst)[1] = make_float4(o.obs[2], o.obs[3], __int_as_float(s.k), __int_as_float(reset));
+}
+
+// Observations from pose records (optionally gathered through `index`): the same cast_walls / normalisation
+// code as env_step, so the result is bit-identical to the observation the rollout would have written.
+template <int U>
+__global__ void __launch_bounds__(kBlock)
+k_observe(const __grid_constant__ TrackParams P, const Tables G, long long n, const PoseRec *__restrict__ poses,
+          const long long *__restrict__ index, float *__restrict__ obs_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PoseRec *src = poses + (index ? index[i] : i);
+    const double2 p = reinterpret_cast<const double2 *>(src)[0];
+    const float4 q = reinterpret_cast<const float4 *>(src)[1];
+    float obs[kObsDim];
+    if (__float_as_int(q.w) != 0) {
+#pragma unroll
+        for (int k = 0; k < kObsDim; ++k) obs[k] = P.reset_obs[k];
+    } else {
+        EnvState s;
+        s.px = p.x; s.py = p.y; s.vx = 0.0; s.vy = 0.0;
+        s.k = __float_as_int(q.z); s.t = 0; s.next_gate = 0; s.passed = 0;
+        float dist[kNumRays];
+        cast_walls<U>(s, P, T, dist, nullptr);
+        pose_observation(s, q.x, q.y, dist, T, obs);
+    }
+    float2 *dst = reinterpret_cast<float2 *>(obs_out + (size_t)i * kObsDim);
+#pragma unroll
+    for (int k = 0; k < kObsDim / 2; ++k) dst[k] = make_float2(obs[2 * k], obs[2 * k + 1]);
+}
+
 #ifndef CARENV_MIN_BLOCKS
 #define CARENV_MIN_BLOCKS 4
 #endif
@@ -120,7 +160,7 @@ __global__ void __launch_bounds__(kBlock, CARENV_MIN_BLOCKS)
 k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int n_steps, double2 *__restrict__ pos,
           double2 *__restrict__ vel, int4 *__restrict__ ints, const ActT *__restrict__ actions, double reward_scale,
           float *__restrict__ obs_out, float *__restrict__ rew_out, FlagT *__restrict__ term_out,
-          FlagT *__restrict__ trunc_out, int4 *__restrict__ info_out, unsigned long long *stats) {
+          FlagT *__restrict__ trunc_out, int4 *__restrict__ info_out, unsigned long long *stats, int obs_mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,10 +180,12 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
         if (t + 1 < n_steps) a_next = (int)actions[idx + (size_t)n_envs];   // next step's action is in flight during this step
         StepResult o;
         env_step<U>(s, a, reward_scale, P, T, o, stats);
-        if (obs_out) {
+        if (obs_mode == kObsFull) {
             float2 *dst = reinterpret_cast<float2 *>(obs_out + idx * kObsDim);
 #pragma unroll
             for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(o.obs[2 * i], o.obs[2 * i + 1]);
+        } else if (obs_mode == kObsPose) {                   // 32-byte pose record instead of the 72-byte observation
+            store_pose(reinterpret_cast<PoseRec *>(obs_out) + idx, s, o);
         }
         rew_out[idx] = o.reward;
         term_out[idx] = make_flag<FlagT>(o.terminated);
@@ -624,7 +666,7 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
 template <typename ActT, typename FlagT, int U>
 int launch_rollout_t(Handle *h, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints, const void *actions,
                    double reward_scale, float *obs_out, float *reward_out, void *term_out, void *trunc_out,
-                   int32_t *info_out, cudaStream_t stream) {
+                   int32_t *info_out, cudaStream_t stream, int obs_mode) {
     auto kern = k_rollout<ActT, FlagT, U>;
     const int block = h->block > 0 ? h->block : kBlock;
     const size_t smem = h->smem_bytes + (size_t)h->smem_pad;
@@ -635,7 +677,7 @@ int launch_rollout_t(Handle *h, int n_envs, int n_steps, double *pos, double *ve
         h->host.P, h->dev, n_envs, n_steps, reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel),
         reinterpret_cast<int4 *>(ints), static_cast<const ActT *>(actions), reward_scale, obs_out, reward_out,
         static_cast<FlagT *>(term_out), static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out),
-        h->d_stats);
+        h->d_stats, obs_mode);
     CU(cudaGetLastError());
     return 0;
 }
@@ -644,11 +686,11 @@ int launch_rollout_t(Handle *h, int n_envs, int n_steps, double *pos, double *ve
 template <typename ActT, typename FlagT>
 int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints, const void *actions,
                    double reward_scale, float *obs_out, float *reward_out, void *term_out, void *trunc_out,
-                   int32_t *info_out, cudaStream_t stream) {
+                   int32_t *info_out, cudaStream_t stream, int obs_mode) {
     int U = h->force_generic ? 1 : h->host.P.unroll;
     if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
     if (h->host.P.n_seg > kMaxSeg) U = 0;                   // geometry from shared memory
-#define ARGS h, n_envs, n_steps, pos, vel, ints, actions, reward_scale, obs_out, reward_out, term_out, trunc_out, info_out, stream
+#define ARGS h, n_envs, n_steps, pos, vel, ints, actions, reward_scale, obs_out, reward_out, term_out, trunc_out, info_out, stream, obs_mode
     if (U == 6) return launch_rollout_t<ActT, FlagT, 6>(ARGS);
     if (U == 4) return launch_rollout_t<ActT, FlagT, 4>(ARGS);
     if (U == 2) return launch_rollout_t<ActT, FlagT, 2>(ARGS);
@@ -659,11 +701,13 @@ int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel,
 
 int dispatch_rollout(void *handle, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints,
                      const void *actions, int action_dtype, double reward_scale, float *obs_out, float *reward_out,
-                     void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream) {
+                     void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream,
+                     int obs_mode) {
     Handle *h = static_cast<Handle *>(handle);
     if (!h) return fail(CARENV_E_INVAL, "null handle");
     if (n_envs < 0 || n_steps < 0) return fail(CARENV_E_INVAL, "negative n_envs / n_steps");
     if (n_envs == 0 || n_steps == 0) return 0;
+    if (!obs_out) obs_mode = kObsNone;
     if (!pos || !vel || !ints || !actions || !reward_out || !term_out || !trunc_out)
         return fail(CARENV_E_INVAL, "null state / action / output pointer");
     DeviceGuard guard(h->device);
@@ -672,7 +716,7 @@ int dispatch_rollout(void *handle, int n_envs, int n_steps, double *pos, double 
 #define CASE(A, AT, F, FT)                                                                                       \
     if (action_dtype == A && flag_dtype == F)                                                                    \
         return launch_rollout<AT, FT>(h, n_envs, n_steps, pos, vel, ints, actions, reward_scale, obs_out,       \
-                                      reward_out, term_out, trunc_out, info_out, st);
+                                      reward_out, term_out, trunc_out, info_out, st, obs_mode);
     CASE(CARENV_ACT_U8, uint8_t, CARENV_FLAG_U8, uint8_t)
     CASE(CARENV_ACT_U8, uint8_t, CARENV_FLAG_F32, float)
     CASE(CARENV_ACT_I32, int32_t, CARENV_FLAG_U8, uint8_t)
@@ -787,14 +831,50 @@ int carenv_step(void *handle, int n_envs, double *pos, double *vel, int32_t *int
                 void *trunc_out, int flag_dtype, int32_t *info_out, void *stream) {
     if (!obs_out) return fail(CARENV_E_INVAL, "carenv_step needs obs_out");
     return dispatch_rollout(handle, n_envs, 1, pos, vel, ints, actions, action_dtype, reward_scale, obs_out,
-                            reward_out, term_out, trunc_out, flag_dtype, info_out, stream);
+                            reward_out, term_out, trunc_out, flag_dtype, info_out, stream, kObsFull);
 }
 
 int carenv_rollout(void *handle, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints,
                    const void *actions, int action_dtype, double reward_scale, float *obs_out, float *reward_out,
                    void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream) {
     return dispatch_rollout(handle, n_envs, n_steps, pos, vel, ints, actions, action_dtype, reward_scale, obs_out,
-                            reward_out, term_out, trunc_out, flag_dtype, info_out, stream);
+                            reward_out, term_out, trunc_out, flag_dtype, info_out, stream, kObsFull);
+}
+
+int carenv_rollout_poses(void *handle, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints,
+                         const void *actions, int action_dtype, double reward_scale, void *pose_out, float *reward_out,
+                         void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream) {
+    if (!pose_out) return fail(CARENV_E_INVAL, "carenv_rollout_poses needs pose_out");
+    static_assert(sizeof(PoseRec) == CARENV_POSE_BYTES, "header and kernel disagree on the pose record");
+    return dispatch_rollout(handle, n_envs, n_steps, pos, vel, ints, actions, action_dtype, reward_scale,
+                            static_cast<float *>(pose_out), reward_out, term_out, trunc_out, flag_dtype, info_out,
+                            stream, kObsPose);
+}
+
+int carenv_observe(void *handle, long long n, const void *poses, const long long *index, float *obs_out,
+                   void *stream) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(CARENV_E_INVAL, "null handle");
+    if (n < 0 || n > 0x7fffffffLL * 128) return fail(CARENV_E_INVAL, "bad record count");
+    if (n == 0) return 0;
+    if (!poses || !obs_out) return fail(CARENV_E_INVAL, "null pointer");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    int U = h->force_generic ? 1 : h->host.P.unroll4;
+    if (h->host.P.n_seg > kMaxSeg) U = 0;
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    auto launch = [&](auto kern) -> int {
+        if (h->smem_bytes > 48 * 1024)
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        kern<<<grid, kBlock, h->smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+            h->host.P, h->dev, n, static_cast<const PoseRec *>(poses), index, obs_out);
+        CU(cudaGetLastError());
+        return 0;
+    };
+    if (U == 4) return launch(k_observe<4>);
+    if (U == 2) return launch(k_observe<2>);
+    if (U == 0) return launch(k_observe<0>);
+    return launch(k_observe<1>);
 }
 
 int carenv_policy_weights_floats(void) { return kPolicyFloats; }

@@ -224,10 +224,19 @@ class VecCarEnv:
 
     # ------------------------------------------------------------------ multi-step launch
     def rollout(self, actions: torch.Tensor, obs_out=None, reward_out=None, term_out=None, trunc_out=None,
-                info_out=None, store_obs: bool = True, store_info: bool = False):
+                info_out=None, store_obs: bool = True, store_info: bool = False, store_poses: bool = False,
+                pose_out=None):
         """n_steps consecutive steps in one kernel launch (the rollout loop of train.py:173-195 with
         the actions given up front).  ``actions`` is a CUDA tensor [n_steps, n_envs]; outputs are
-        [n_steps, n_envs(, 18)] CUDA tensors (allocated here unless passed in)."""
+        [n_steps, n_envs(, 18)] CUDA tensors (allocated here unless passed in).
+
+        ``store_poses=True`` (or ``pose_out``) stores a 32-byte pose record per env-step instead of the
+        72-byte observation (out["poses"], an opaque float64 tensor [n_steps, n_envs, 4]); ``observe`` turns
+        records back into observations, bit-identical to the ones this call would have stored."""
+        if store_poses or pose_out is not None:
+            store_obs, store_poses = False, True
+            if obs_out is not None:
+                raise ValueError("pass either obs_out or pose_out / store_poses")
         if self._needs_reset:
             raise _lib.CarEnvError("call reset() before rollout()")
         if not (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dim() == 2):
@@ -250,22 +259,47 @@ class VecCarEnv:
             trunc_out = torch.empty((K, n), dtype=fdt, device=dev)
         if info_out is None and store_info:
             info_out = torch.empty((K, n, 4), dtype=torch.int32, device=dev)
+        if pose_out is None and store_poses:
+            pose_out = torch.empty((K, n, 4), dtype=torch.float64, device=dev)
         for name, t, shape, dt in (("obs_out", obs_out, (K, n, OBS_DIM), torch.float32),
+                                   ("pose_out", pose_out, (K, n, 4), torch.float64),
                                    ("reward_out", reward_out, (K, n), torch.float32),
                                    ("term_out", term_out, (K, n), fdt), ("trunc_out", trunc_out, (K, n), fdt),
                                    ("info_out", info_out, (K, n, 4), torch.int32)):
             if t is not None and (tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or not t.is_cuda):
                 raise ValueError(f"{name} must be a contiguous CUDA tensor of shape {shape} and dtype {dt}")
         with torch.cuda.device(dev):
-            rc = self._L.carenv_rollout(self._handle, n, K, _ptr(self.pos), _ptr(self.vel), _ptr(self.ints),
-                                        _ptr(actions), _ACT_CODES[actions.dtype], self.reward_scaling, _ptr(obs_out),
-                                        _ptr(reward_out), _ptr(term_out), _ptr(trunc_out),
-                                        _lib.FLAG_F32 if self.float_flags else _lib.FLAG_U8, _ptr(info_out),
-                                        self._stream())
-        _lib.check(rc, "carenv_rollout")
+            fn = self._L.carenv_rollout_poses if store_poses else self._L.carenv_rollout
+            rc = fn(self._handle, n, K, _ptr(self.pos), _ptr(self.vel), _ptr(self.ints), _ptr(actions),
+                    _ACT_CODES[actions.dtype], self.reward_scaling, _ptr(pose_out if store_poses else obs_out),
+                    _ptr(reward_out), _ptr(term_out), _ptr(trunc_out),
+                    _lib.FLAG_F32 if self.float_flags else _lib.FLAG_U8, _ptr(info_out), self._stream())
+        _lib.check(rc, "carenv_rollout_poses" if store_poses else "carenv_rollout")
         out = {"obs": obs_out, "reward": reward_out, "terminated": term_out, "truncated": trunc_out}
+        if store_poses:
+            out["poses"] = pose_out
         if info_out is not None:
             out["info"] = self._info_dict(info_out)
+        return out
+
+    def observe(self, poses: torch.Tensor, index: torch.Tensor | None = None, out: torch.Tensor | None = None):
+        """Observations [M, 18] float32 from pose records (``rollout(..., store_poses=True)["poses"]``, any leading
+        shape): all records in order, or the records ``index`` (int64, into the flattened record array) names —
+        the minibatch gather of train.py:233 without ever materialising the [T, N, 18] observation buffer."""
+        if not (poses.is_cuda and poses.dtype == torch.float64 and poses.shape[-1] == 4 and poses.is_contiguous()):
+            raise ValueError("poses must be a contiguous CUDA float64 tensor [..., 4] from rollout(store_poses=True)")
+        if index is not None:
+            if not (index.is_cuda and index.dtype == torch.int64):
+                raise ValueError("index must be a CUDA int64 tensor")
+            index = index.reshape(-1).contiguous()
+        m = index.numel() if index is not None else poses.numel() // 4
+        if out is None:
+            out = torch.empty((m, OBS_DIM), dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != (m, OBS_DIM) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 tensor of shape {(m, OBS_DIM)}")
+        with torch.cuda.device(self.device):
+            rc = self._L.carenv_observe(self._handle, m, _ptr(poses), _ptr(index), _ptr(out), self._stream())
+        _lib.check(rc, "carenv_observe")
         return out
 
     def set_option(self, name: str, value: int) -> None:

@@ -391,3 +391,38 @@ def test_multi_track_vector_env(tracks_dir):
         assert torch.equal(te[:300], te1) and torch.equal(te[300:], te2)
         assert torch.equal(info["gates_passed"][300:], i2["gates_passed"])
     multi.close()
+
+
+@pytest.mark.parametrize("name,n_envs", [("big_track", 4099), ("track", 1500)])
+def test_pose_records_reproduce_observations_bit_for_bit(tracks_dir, name, n_envs):
+    """a rollout that stores 32-byte pose records instead of 72-byte observations, and
+    carenv_observe turning records (all, or a gathered minibatch) back into the very same observations."""
+    path = os.path.join(tracks_dir, name + ".json")
+    T = 400
+    g = torch.Generator(device="cuda").manual_seed(21)
+    acts = torch.randint(0, 9, (T, n_envs), generator=g, device="cuda", dtype=torch.uint8)
+    acts[:, : n_envs // 8] = 0                                # full throttle: collisions within ~30 steps
+    acts[:, n_envs // 8: n_envs // 4] = 8                     # idle: truncation at 1000 is not reached, no resets
+    ref = ppo_car_b200.VecCarEnv(n_envs, path, reward_scaling=0.1)
+    ref.reset()
+    full = ref.rollout(acts)
+    env = ppo_car_b200.VecCarEnv(n_envs, path, reward_scaling=0.1)
+    env.reset()
+    out = env.rollout(acts, store_poses=True)
+    assert out["obs"] is None and out["poses"].shape == (T, n_envs, 4) and out["poses"].dtype == torch.float64
+    for k in ("reward", "terminated", "truncated"):
+        assert torch.equal(out[k], full[k])
+    done = (full["terminated"] | full["truncated"]).bool()
+    assert int(done.sum()) > n_envs // 8
+    obs = env.observe(out["poses"])
+    assert torch.equal(obs.view(T, n_envs, 18), full["obs"])
+    idx = torch.randint(0, T * n_envs, (512,), generator=g, device="cuda")
+    assert torch.equal(env.observe(out["poses"], idx), full["obs"].view(-1, 18)[idx])
+    buf = torch.empty((512, 18), device="cuda")
+    assert env.observe(out["poses"], idx, out=buf) is buf
+    with pytest.raises(ValueError):
+        env.observe(out["poses"].float())
+    with pytest.raises(ValueError):
+        env.rollout(acts, obs_out=full["obs"], store_poses=True)
+    # the slow path (rays through vertices, collision band) takes the same decisions in both kernels
+    assert torch.equal(env.pos, ref.pos) and torch.equal(env.ints, ref.ints)

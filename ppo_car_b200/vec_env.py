@@ -19,6 +19,7 @@ Two calling conventions for ``step``:
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -179,7 +180,9 @@ class VecCarEnv:
         dev = self.device
         if self._host is None:
             pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
-            n_chunks = 4 if n >= 131072 else 1
+            # ~65,536 envs (6 MB of results) per sub-range, at most 8: measured best on B200 / PCIe 5 (1 M envs:
+            # 8 ranges 2.07 ms per step, 4: 2.15, 1: 2.52; 131,072 envs: 2 ranges 0.37 ms, 4: 0.50, 1: 0.40)
+            n_chunks = int(os.environ.get("CARENV_HOST_CHUNKS", 0)) or max(1, min(8, n // 65536))
             edges = [round(i * n / n_chunks) for i in range(n_chunks + 1)]
             self._host = dict(act=pin((n,), torch.uint8), obs=pin((n, OBS_DIM), torch.float32),
                               rew=pin((n,), torch.float32), term=pin((n,), self._term.dtype),

@@ -89,6 +89,8 @@ def parse_args(argv=None):
     p.add_argument("--fused-rollout", action="store_true",
                    help="run the whole rollout (policy forward, sampling, env step, buffer rows) in ONE kernel launch "
                         "per epoch (carenv_policy_rollout); needs the reference network shape")
+    p.add_argument("--fused-cuda-cores", action="store_true",
+                   help="with --fused-rollout: use the CUDA-core kernel instead of the tensor-core one")
     p.add_argument("--graph-update", action="store_true",
                    help="capture one minibatch update (sampling, forward, backward, clip, Adam) in a CUDA graph and "
                         "replay it train_iters x minibatches times per epoch (the NCCL gradient all-reduce is captured too)")
@@ -152,9 +154,9 @@ def train(args) -> list[dict]:
     if args.fused_rollout:
         from .policy import fused_rollout, pack_policy_weights, pack_policy_weights_tc
 
-        # tensor-core kernel (256- or 512-environment CTAs, chosen by the library from the shard size) from 4,096
-        # environments per shard (benchmarks/fused_tiles.py), CUDA-core kernel (128-thread CTAs) below
-        pack_policy = pack_policy_weights_tc if n >= 4096 else pack_policy_weights
+        # tensor-core kernel (256- or 512-environment CTAs, chosen by the library from the shard size); it is also
+        # the faster one for tiny shards (24 envs: 12.7 vs 14.4 us per step, benchmarks/fused_rollout.py)
+        pack_policy = pack_policy_weights_tc if not args.fused_cuda_cores else pack_policy_weights
         packed = pack_policy(agent.actor, agent.critic)
         last_val = torch.empty(n, device=dev)
 

@@ -90,8 +90,10 @@ def test_fused_rollout_matches_torch_policy_and_env_kernel(tracks_dir, n, tensor
 
 
 @pytest.mark.gpu
-def test_training_with_fused_rollout_improves_reward():
-    args = parse_args(["--track", "big_track", "--n-envs", "64", "--n-epochs", "12", "--n-steps", "256", "--fused-rollout"])
+@pytest.mark.parametrize("extra", [[], ["--fused-cuda-cores"]])
+def test_training_with_fused_rollout_improves_reward(extra):
+    args = parse_args(["--track", "big_track", "--n-envs", "64", "--n-epochs", "12", "--n-steps", "256",
+                       "--fused-rollout"] + extra)
     hist = train(args)
     assert all(math.isfinite(h["total_loss"]) for h in hist)
     assert hist[-1]["avg_reward"] > hist[0]["avg_reward"] + 0.03

@@ -2,7 +2,7 @@
 """Time the BASELINE.json configs that bench.py does not headline (one JSON object per config).
 
   config 2   tracks/big_track.json, 24 envs x 1024 steps, random actions, one rollout launch
-  config 3   big_track.json, 65,536 envs x 1024 steps rollout (32-step launches, every step stored in
+  config 3   big_track.json, 65,536 envs x 1024 steps rollout (one 1,024-step launch, every step stored in
              the [1024, 65536, 18] buffer) + GAE over [1024, 65536]
   step API   VecCarEnv.step with device actions at 24 / 65,536 / 1,048,576 envs (one launch per step)
 
@@ -43,7 +43,7 @@ ms = timed(lambda: env.rollout(acts), 5)
 print(json.dumps({"config": "2: big_track, 24 envs x 1024 steps, one launch", "ms": ms, "env_steps_per_s": n * T / ms * 1e3}))
 
 # ---- config 3
-n, T, chunk = 65536, 1024, 32
+n, T, chunk = 65536, 1024, 1024
 env = ppo_car_b200.VecCarEnv(n, track, float_flags=True)
 env.reset()
 buf = ppo_car_b200.Buffer((18,), T, n, dev)

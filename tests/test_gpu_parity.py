@@ -426,3 +426,23 @@ def test_pose_records_reproduce_observations_bit_for_bit(tracks_dir, name, n_env
         env.rollout(acts, obs_out=full["obs"], store_poses=True)
     # the slow path (rays through vertices, collision band) takes the same decisions in both kernels
     assert torch.equal(env.pos, ref.pos) and torch.equal(env.ints, ref.ints)
+
+
+def test_reset_with_track_path_switches_the_track_mid_run(golden_dir, tracks_dir):
+    """CarEnv.reset(options={"track_path": ...}) (lib/car_env.py:621-628, train.py:159): an env that has been
+    stepping on one track is reset onto the other one and then follows that track's golden trajectories."""
+    g = np.load(os.path.join(golden_dir, "carenv_big_track.npz"))
+    acts = g["lap_actions"]
+    env = ppo_car_b200.VecCarEnv(acts.shape[1], os.path.join(tracks_dir, "track.json"))
+    env.reset()
+    env.rollout(torch.randint(0, 9, (50, acts.shape[1]), device="cuda", dtype=torch.uint8))
+    with pytest.raises(ppo_car_b200.CarEnvError):
+        env._set_track(os.path.join(tracks_dir, "big_track.json")) or env.step(acts[0])   # new track: reset first
+    obs0, _ = env.reset(options={"track_path": os.path.join(tracks_dir, "big_track.json")})
+    assert_floats_close(obs0.cpu().numpy(), np.broadcast_to(g["reset_obs"], obs0.shape), "reset obs")
+    out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
+    done = (g["lap_term"] | g["lap_trunc"]).astype(bool)
+    ref = dict(obs=np.where(done[..., None], g["reset_obs"], g["lap_final_obs"]), rew=g["lap_rew"], term=g["lap_term"],
+               trunc=g["lap_trunc"], gates_passed=g["lap_gates_passed"], time_passed=g["lap_time_passed"],
+               next_gate_index=g["lap_next_gate_index"])
+    assert_trajectory_matches(_gpu_traj(out), ref, what="big_track/lap after a track switch")

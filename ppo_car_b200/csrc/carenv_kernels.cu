@@ -1017,13 +1017,17 @@ int gae_reverse_scan(const float *rew, const float *val, const float *term, cons
         return fail(CARENV_E_INVAL, "null pointer");
     const float g = (float)gamma;
     const float gl = (float)(gamma * gae_lambda);   // evaluated in double first (lib/buffer.py:61)
-    const int grid = (N + 127) / 128;
-    if (N >= 100000)
-        k_gae<16><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(rew, val, term, trunc, last_val, last_term,
-                                                                     last_trunc, adv, ret, T, N, g, gl);
+    // 64-thread blocks: 1,024 blocks at N = 65,536 balance over 148 SMs (6.9 per SM) better than 512 blocks of 128
+    // (3.5 per SM): 6.05 vs 5.93 TB/s measured at [1024, 65536]
+    const int block = 64;
+    const int grid = (N + block - 1) / block;
+    const bool wide = N >= 100000;
+    if (wide)
+        k_gae<16><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(rew, val, term, trunc, last_val, last_term,
+                                                                       last_trunc, adv, ret, T, N, g, gl);
     else
-        k_gae<8><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(rew, val, term, trunc, last_val, last_term,
-                                                                    last_trunc, adv, ret, T, N, g, gl);
+        k_gae<8><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(rew, val, term, trunc, last_val, last_term,
+                                                                      last_trunc, adv, ret, T, N, g, gl);
     CU(cudaGetLastError());
     return 0;
 }

@@ -103,8 +103,10 @@ int carenv_rollout_poses(void *handle, int n_envs, int n_steps, double *pos, dou
                          void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream);
 int carenv_observe(void *handle, long long n, const void *poses, const long long *index, float *obs_out, void *stream);
 
-/* Tuning / test options.  "force_generic" = 1 runs the generic segment loop even for tracks that have
- * a fully unrolled kernel instantiation (the two produce identical results). */
+/* Options.  "pose_rows" = 1: the fused rollout kernels below write 32-byte pose records (see
+ * carenv_rollout_poses) through their obs_buf argument instead of observations.  Tuning / test hooks:
+ * "force_generic" = 1 runs the generic segment loop even for tracks that have an unrolled kernel instantiation
+ * (identical results); "max_unroll", "block", "smem_pad", "tc_tiles" select kernel variants for measurements. */
 int carenv_set_option(void *handle, const char *name, int value);
 
 /* Slow-path counters since the last reset of the counters: [0] lines re-evaluated in float64

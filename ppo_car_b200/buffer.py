@@ -43,14 +43,19 @@ def gae_reverse_scan(rew, val, term, trunc, last_val, last_term, last_trunc, gam
 class Buffer:
     """Buffer for storing trajectories (drop-in for lib.buffer.Buffer)."""
 
-    def __init__(self, obs_dim, size, num_envs, device, gamma=0.99, gae_lambda=0.95):
+    def __init__(self, obs_dim, size, num_envs, device, gamma=0.99, gae_lambda=0.95, compact_obs=False):
+        """``compact_obs=True`` (no counterpart in the reference): no [size, num_envs, 18] observation
+        tensor; ``pose_buf`` [size, num_envs, 4] float64 holds one 32-byte pose record per row instead, written by
+        ``fused_rollout`` and turned back into observations by ``VecCarEnv.observe(pose_buf, index)``."""
         device = torch.device(device)
         if device.type != "cuda":
             raise _lib.CarEnvError("ppo_car_b200.Buffer lives on a CUDA device (there is no CPU implementation)")
         _lib.lib()
         self.capacity = size
         z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=device)
-        self.obs_buf = z(size, num_envs, *obs_dim)
+        self.compact_obs = bool(compact_obs)
+        self.obs_buf = None if compact_obs else z(size, num_envs, *obs_dim)
+        self.pose_buf = torch.zeros((size, num_envs, 4), dtype=torch.float64, device=device) if compact_obs else None
         self.act_buf = z(size, num_envs)
         self.rew_buf = z(size, num_envs)
         self.val_buf = z(size, num_envs)
@@ -63,6 +68,8 @@ class Buffer:
 
     def store(self, obs, act, rew, val, term, trunc, logprob):
         """Store one step; first dimension is the step, second the environment (lib/buffer.py:22-34)."""
+        if self.compact_obs:
+            raise _lib.CarEnvError("a compact_obs Buffer is filled by fused_rollout (pose records), not by store()")
         p = self.ptr
         self.obs_buf[p] = obs
         self.act_buf[p] = act
@@ -84,7 +91,8 @@ class Buffer:
                                     adv_out=self._adv, ret_out=self._ret)
 
     def get(self):
-        """obs_buf, act_buf, val_buf, logprob_buf; rewinds the write pointer (lib/buffer.py:66-73)."""
+        """obs_buf (pose_buf if compact_obs), act_buf, val_buf, logprob_buf; rewinds the write pointer
+        (lib/buffer.py:66-73)."""
         assert self.ptr == self.capacity
         self.ptr = 0
-        return self.obs_buf, self.act_buf, self.val_buf, self.logprob_buf
+        return (self.pose_buf if self.compact_obs else self.obs_buf), self.act_buf, self.val_buf, self.logprob_buf

@@ -53,6 +53,7 @@ struct Handle {
     int block;                // tuning hook: threads per block of k_rollout (0 = chosen per launch, see rollout_block)
     int smem_pad;             // tuning hook: extra dynamic shared memory per block (limits resident blocks per SM)
     int tc_tiles;             // tuning hook: 128-env groups per CTA of k_policy_rollout_tc (0 = chosen per launch)
+    int pose_rows;            // fused rollout kernels: obs_buf holds 32-byte pose records instead of observations
 };
 
 struct DeviceGuard {
@@ -115,11 +116,13 @@ __device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, int
 // What k_rollout writes per env-step besides reward and flags (rollout storage format).
 enum { kObsNone = 0, kObsFull = 1, kObsPose = 2 };
 
-__device__ __forceinline__ void store_pose(PoseRec *dst, const EnvState &s, const StepResult &o) {
-    const int reset = o.terminated | o.truncated;            // the observation of this row is the reset observation
+// The pose behind an observation: `s` is the state the observation was computed from, obs2 / obs3 its velocity
+// entries.  time_step == 0 only in the start state (after reset or autoreset), whose observation is the reset
+// observation (evaluated with the literal float64 formulas, not recomputable by the float32 path).
+__device__ __forceinline__ void store_pose(PoseRec *dst, const EnvState &s, float obs2, float obs3) {
     double2 *d2 = reinterpret_cast<double2 *>(dst);
     d2[0] = make_double2(s.px, s.py);
-    reinterpret_cast<float4 *>(dst)[1] = make_float4(o.obs[2], o.obs[3], __int_as_float(s.k), __int_as_float(reset));
+    reinterpret_cast<float4 *>(dst)[1] = make_float4(obs2, obs3, __int_as_float(s.k), __int_as_float(s.t == 0 ? 1 : 0));
 }
 
 // Observations from pose records (optionally gathered through `index`): the same cast_walls / normalisation
@@ -185,7 +188,7 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
 #pragma unroll
             for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(o.obs[2 * i], o.obs[2 * i + 1]);
         } else if (obs_mode == kObsPose) {                   // 32-byte pose record instead of the 72-byte observation
-            store_pose(reinterpret_cast<PoseRec *>(obs_out) + idx, s, o);
+            store_pose(reinterpret_cast<PoseRec *>(obs_out) + idx, s, o.obs[2], o.obs[3]);
         }
         rew_out[idx] = o.reward;
         term_out[idx] = make_flag<FlagT>(o.terminated);
@@ -259,7 +262,7 @@ k_policy_rollout(const __grid_constant__ TrackParams P, const Tables G, const fl
                  double reward_scale, float *__restrict__ obs_buf, float *__restrict__ act_buf,
                  float *__restrict__ rew_buf, float *__restrict__ val_buf, float *__restrict__ term_buf,
                  float *__restrict__ trunc_buf, float *__restrict__ logp_buf, float *__restrict__ last_val,
-                 float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes) {
+                 float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes, int obs_mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     float *sw = reinterpret_cast<float *>(smem + table_bytes);
     for (int i = threadIdx.x; i < kPolicyFloats / 4; i += blockDim.x)
@@ -293,7 +296,9 @@ k_policy_rollout(const __grid_constant__ TrackParams P, const Tables G, const fl
         const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
         float logp, us;
         const int a = sample_action(po, u, logp, us);
-        {
+        if (obs_mode == kObsPose) {
+            store_pose(reinterpret_cast<PoseRec *>(obs_buf) + idx, s, obs[2], obs[3]);
+        } else {
             float2 *dst = reinterpret_cast<float2 *>(obs_buf + idx * kObsDim);
 #pragma unroll
             for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
@@ -353,7 +358,7 @@ k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const
                     double reward_scale, float *__restrict__ obs_buf, float *__restrict__ act_buf,
                     float *__restrict__ rew_buf, float *__restrict__ val_buf, float *__restrict__ term_buf,
                     float *__restrict__ trunc_buf, float *__restrict__ logp_buf, float *__restrict__ last_val,
-                    float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes) {
+                    float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes, int obs_mode) {
     constexpr int kTcTiles = TILES;                          // 128-env groups per CTA (+ one MMA-issuing warp)
     constexpr int kTcCols = 512 / TILES;                     // accumulator columns per group and round
     constexpr int kTcRounds = kHidden / kTcCols;             // rounds per net
@@ -530,9 +535,13 @@ k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const
             float logp, us;
             const int a = sample_action(po, u, logp, us);
             if (active) {
-                float2 *dst = reinterpret_cast<float2 *>(obs_buf + idx * kObsDim);
+                if (obs_mode == kObsPose) {
+                    store_pose(reinterpret_cast<PoseRec *>(obs_buf) + idx, s, obs[2], obs[3]);
+                } else {
+                    float2 *dst = reinterpret_cast<float2 *>(obs_buf + idx * kObsDim);
 #pragma unroll
-                for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+                    for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+                }
                 act_buf[idx] = (float)a;
                 val_buf[idx] = po.value;
                 logp_buf[idx] = logp;
@@ -748,7 +757,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -906,7 +915,7 @@ int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs,
             h->host.P, h->dev, packed_weights, n_envs, n_steps, env_offset, seed, step0,
             reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints), cur_obs,
             cur_term, cur_trunc, reward_scale, obs_buf, act_buf, rew_buf, val_buf, term_buf, trunc_buf, logp_buf,
-            last_val, u_dbg, h->d_stats, table_bytes);
+            last_val, u_dbg, h->d_stats, table_bytes, h->pose_rows ? kObsPose : kObsFull);
         CU(cudaGetLastError());
         return 0;
     };
@@ -963,7 +972,7 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
             h->host.P, h->dev, packed_weights, n_envs, n_steps, env_offset, seed, step0,
             reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints), cur_obs,
             cur_term, cur_trunc, reward_scale, obs_buf, act_buf, rew_buf, val_buf, term_buf, trunc_buf, logp_buf,
-            last_val, u_dbg, h->d_stats, table_bytes);
+            last_val, u_dbg, h->d_stats, table_bytes, h->pose_rows ? kObsPose : kObsFull);
         CU(cudaGetLastError());
         return 0;
     };
@@ -986,6 +995,7 @@ int carenv_set_option(void *handle, const char *name, int value) {
         if (value < 0 || value > kBlock || value % 32) return fail(CARENV_E_INVAL, "block must be 0, 32, 64, 96 or 128");
         h->block = value; return 0;
     }
+    if (std::string(name) == "pose_rows") { h->pose_rows = value ? 1 : 0; return 0; }
     if (std::string(name) == "tc_tiles") {
         if (value != 0 && value != 2 && value != 4) return fail(CARENV_E_INVAL, "tc_tiles must be 0, 2 or 4");
         h->tc_tiles = value; return 0;

@@ -102,8 +102,11 @@ def fused_rollout(env, packed: torch.Tensor, buf, cur_obs: torch.Tensor, cur_ter
         if t is not None and (tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_contiguous()
                               or t.device != env.device):
             raise ValueError(f"{name} must be a contiguous float32 tensor of shape {shape} on {env.device}")
-    if tuple(buf.obs_buf.shape) != (T, n, OBS):
+    compact = bool(getattr(buf, "compact_obs", False))
+    rows = buf.pose_buf if compact else buf.obs_buf
+    if tuple(rows.shape) != ((T, n, 4) if compact else (T, n, OBS)):
         raise ValueError("buffer shape does not match the environment")
+    env.set_option("pose_rows", int(compact))               # obs_buf argument = 32-byte pose records
     L = _lib.lib()
     if tensor_cores is None:                                # the two packings have different sizes
         tensor_cores = packed.numel() == L.carenv_policy_weights_floats_tc()
@@ -111,7 +114,7 @@ def fused_rollout(env, packed: torch.Tensor, buf, cur_obs: torch.Tensor, cur_ter
     with torch.cuda.device(env.device):
         rc = fn(env._handle, _p(packed), n, T, int(env_offset), int(seed) & (2 ** 64 - 1), int(step0), _p(env.pos),
                 _p(env.vel), _p(env.ints), _p(cur_obs), _p(cur_term), _p(cur_trunc), float(env.reward_scaling),
-                _p(buf.obs_buf), _p(buf.act_buf), _p(buf.rew_buf), _p(buf.val_buf), _p(buf.term_buf),
+                _p(rows), _p(buf.act_buf), _p(buf.rew_buf), _p(buf.val_buf), _p(buf.term_buf),
                 _p(buf.trunc_buf), _p(buf.logprob_buf), _p(last_val), _p(u_dbg), env._stream())
     _lib.check(rc, "carenv_policy_rollout_tc" if tensor_cores else "carenv_policy_rollout")
     buf.ptr = T

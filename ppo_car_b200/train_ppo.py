@@ -91,6 +91,9 @@ def parse_args(argv=None):
                         "per epoch (carenv_policy_rollout); needs the reference network shape")
     p.add_argument("--fused-cuda-cores", action="store_true",
                    help="with --fused-rollout: use the CUDA-core kernel instead of the tensor-core one")
+    p.add_argument("--compact-obs", action="store_true",
+                   help="with --fused-rollout: store 32-byte pose records instead of observations and recompute the "
+                        "minibatch observations in the update (VecCarEnv.observe)")
     p.add_argument("--graph-update", action="store_true",
                    help="capture one minibatch update (sampling, forward, backward, clip, Adam) in a CUDA graph and "
                         "replay it train_iters x minibatches times per epoch (the NCCL gradient all-reduce is captured too)")
@@ -127,7 +130,9 @@ def train(args) -> list[dict]:
         opt = torch.optim.Adam(agent.parameters(), lr=args.learning_rate, eps=1e-5)
         sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=args.learning_rate_decay)
     params = [p for p in agent.parameters()]
-    buf = Buffer(obs_dim, T, n, dev, args.gamma, args.gae_lambda)
+    if args.compact_obs and not args.fused_rollout:
+        raise SystemExit("--compact-obs needs --fused-rollout")
+    buf = Buffer(obs_dim, T, n, dev, args.gamma, args.gae_lambda, compact_obs=args.compact_obs)
     torch.manual_seed(args.seed * 1000 + rank + 1)     # different sampling noise per shard
 
     # the rollout state lives in three static tensors so that the loop below can be captured in a graph
@@ -196,7 +201,8 @@ def train(args) -> list[dict]:
         rew_sum, steps, episodes = allreduce_rollout_stats(buf.rew_buf.sum(), torch.tensor(float(T * n), device=dev),
                                                            buf.term_buf.sum() + buf.trunc_buf.sum())
         obs_b, act_b, val_b, logp_b = buf.get()
-        obs_f, act_f, logp_f = obs_b.view(-1, *obs_dim), act_b.view(-1), logp_b.view(-1)
+        obs_f = obs_b if args.compact_obs else obs_b.view(-1, *obs_dim)      # pose records / observations
+        act_f, logp_f = act_b.view(-1), logp_b.view(-1)
         adv_f, ret_f = adv.view(-1), ret.view(-1)
 
         # ---- update (train.py:223-261)
@@ -208,7 +214,8 @@ def train(args) -> list[dict]:
                 """One minibatch: draw indices, clipped-surrogate loss, backward, (all-reduce), clip, Adam."""
                 torch.randint(0, T * n, (args.batch_size,), device=dev, out=idx_static)
                 idx = idx_static
-                _, new_logp, ent, new_val = agent.act(obs_f[idx], act_f[idx])
+                obs_mb = envs.observe(obs_f, idx) if args.compact_obs else obs_f[idx]
+                _, new_logp, ent, new_val = agent.act(obs_mb, act_f[idx])
                 ratio = torch.exp(new_logp - logp_f[idx])
                 a = adv_f[idx]
                 a = (a - a.mean()) / torch.clamp(a.std(), min=1e-5)

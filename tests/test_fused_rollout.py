@@ -128,3 +128,49 @@ def test_tcgen05_gemm_building_block():
     _lib.check(L.carenv_tc_gemm_test(p(A2), p(B2), p(D), st), "carenv_tc_gemm_test")
     torch.cuda.synchronize()
     assert torch.equal(D, A2 @ B2.T)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_fused_rollout_pose_rows_reproduce_the_observation_rows(tracks_dir, tensor_cores):
+    """Buffer(compact_obs=True): the fused kernels write 32-byte pose records instead of observations; observe()
+    gives back exactly the observation rows of an ordinary run with the same seed."""
+    dev = torch.device("cuda")
+    path = os.path.join(tracks_dir, "big_track.json")
+    n, T = 777, 260
+    torch.manual_seed(5)
+    net = ActorCritic(18, 9).to(dev)
+    pack = ppo_car_b200.pack_policy_weights_tc if tensor_cores else ppo_car_b200.pack_policy_weights
+    packed = pack(net.actor, net.critic)
+    bufs, envs = [], []
+    for compact in (False, True):
+        env = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1, float_flags=True)
+        buf = ppo_car_b200.Buffer((18,), T, n, dev, compact_obs=compact)
+        cur_obs = env.reset()[0].clone()
+        cur_term, cur_trunc = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        for part in range(2):                               # the second launch starts from a mid-episode state
+            ppo_car_b200.fused_rollout(env, packed, buf, cur_obs, cur_term, cur_trunc, seed=3, step0=part * T)
+            if part == 0:
+                first = (buf.pose_buf if compact else buf.obs_buf).clone()
+        bufs.append((first, buf))
+        envs.append(env)
+    (obs_first, full), (pose_first, comp) = bufs
+    assert comp.obs_buf is None and comp.pose_buf.shape == (T, n, 4)
+    assert (full.term_buf.sum() + full.trunc_buf.sum()) > n // 4           # episode ends are covered
+    assert torch.equal(envs[1].observe(pose_first).view(T, n, 18), obs_first)
+    assert torch.equal(envs[1].observe(comp.pose_buf).view(T, n, 18), full.obs_buf)
+    for a, b in ((full.act_buf, comp.act_buf), (full.rew_buf, comp.rew_buf), (full.logprob_buf, comp.logprob_buf),
+                 (full.val_buf, comp.val_buf), (full.term_buf, comp.term_buf)):
+        assert torch.equal(a, b)
+    with pytest.raises(ppo_car_b200.CarEnvError):
+        comp.ptr = 0
+        comp.store(None, None, None, None, None, None, None)
+
+
+@pytest.mark.gpu
+def test_training_with_pose_rows_and_graph_update():
+    args = parse_args(["--track", "big_track", "--n-envs", "64", "--n-epochs", "12", "--n-steps", "256",
+                       "--fused-rollout", "--compact-obs", "--graph-update"])
+    hist = train(args)
+    assert all(math.isfinite(h["total_loss"]) for h in hist)
+    assert hist[-1]["avg_reward"] > hist[0]["avg_reward"] + 0.03

@@ -393,11 +393,17 @@ def test_multi_track_vector_env(tracks_dir):
     multi.close()
 
 
-@pytest.mark.parametrize("name,n_envs", [("big_track", 4099), ("track", 1500)])
-def test_pose_records_reproduce_observations_bit_for_bit(tracks_dir, name, n_envs):
+@pytest.mark.parametrize("name,n_envs", [("big_track", 4099), ("track", 1500), ("ring 90+80", 700), ("ring 7+5", 300)])
+def test_pose_records_reproduce_observations_bit_for_bit(tracks_dir, tmp_path, name, n_envs):
     """a rollout that stores 32-byte pose records instead of 72-byte observations, and
     carenv_observe turning records (all, or a gathered minibatch) back into the very same observations."""
-    path = os.path.join(tracks_dir, name + ".json")
+    if name.startswith("ring"):                              # 170 segments: geometry from shared memory; 12: generic loop
+        from tests.synth_tracks import ring_track
+
+        n_outer, n_inner = (int(v) for v in name.split()[1].split("+"))
+        path = ring_track(str(tmp_path / "ring.json"), n_outer, n_inner)
+    else:
+        path = os.path.join(tracks_dir, name + ".json")
     T = 400
     g = torch.Generator(device="cuda").manual_seed(21)
     acts = torch.randint(0, 9, (T, n_envs), generator=g, device="cuda", dtype=torch.uint8)

@@ -385,6 +385,58 @@ CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1
     }
 }
 
+// Warp-per-environment variant (small batches, U = kWarpPerEnv): lane j owns wall segment j — its records live in
+// registers for the whole launch — and evaluates it against the six lines with the arithmetic of wall_point /
+// wall_segment; the per-ray extrema and the guards are then folded over the warp with integer REDUX on the
+// float bit patterns (all positive after a sign flip), which is exact, so the result is bit-identical to the
+// sequential fold of the thread-per-environment kernels.
+constexpr int kWarpPerEnv = -1;
+struct WarpSeg { SegF f; SegD g; int active; };
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float warp_max_pos(float v) {     // v >= 0 in every lane
+    return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
+}
+__device__ __forceinline__ float warp_min_pos(float v) {
+    return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));
+}
+__device__ __forceinline__ void cast_walls_warp(const EnvState &s, const Tables &T, const WarpSeg &ws, float Rp[6],
+                                                float Rm[6], float gq[6], float &gu) {
+    const float R0 = 1.0e-3f;
+    WallAcc w;
+    w.phx = (float)s.px; w.phy = (float)s.py;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const F2 d = T.trig32[wrap72(s.k + 6 * l)];
+        w.c[l] = d.x; w.sn[l] = d.y;
+    }
+    float qa[6], qb[6];
+    wall_point(w, ws.f.ahx, ws.f.ahy, qa);
+    wall_point(w, ws.f.bhx, ws.f.bhy, qb);
+    const float un = (float)dfma(ws.g.ey, s.px, dfma(-ws.g.ex, s.py, ws.g.K));
+    const float inv = frcp(un);
+    const bool on = ws.active != 0;
+    float rp[6], rm[6], g[6];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const float r0 = fmul(ffma(ws.f.ex, w.sn[l], -fmul(ws.f.ey, w.c[l])), inv);
+        const float r3 = fmul(ffma(ws.f.ex, w.c[l], fmul(ws.f.ey, w.sn[l])), inv);
+        const bool h0 = on && fmul(qa[l], qb[l]) < 0.0f, h3 = on && fmul(qa[l + 3], qb[l + 3]) < 0.0f;
+        rp[l] = h0 ? fmaxf(R0, r0) : R0;          rm[l] = h0 ? fminf(-R0, r0) : -R0;
+        rp[l + 3] = h3 ? fmaxf(R0, r3) : R0;      rm[l + 3] = h3 ? fminf(-R0, r3) : -R0;
+    }
+#pragma unroll
+    for (int l = 0; l < 6; ++l) g[l] = on ? fminf(fabsf(qa[l]), fabsf(qb[l])) : 1.0e30f;
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+        Rp[l] = warp_max_pos(rp[l]);
+        Rm[l] = -warp_max_pos(-rm[l]);
+        gq[l] = warp_min_pos(g[l]);
+    }
+    gu = warp_min_pos(on ? fabsf(un) : 1.0e30f);
+}
+#endif
+
 // dist[i] (pixels, float32) for ray i = heading + 30*i degrees; returns destroyed.
 // U = segments per loop iteration.  U > 1 requires (checked on the host, TrackParams::unroll) that
 // n_seg and every polyline start are multiples of U; the body is then U segments of straight-line
@@ -392,10 +444,18 @@ CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1
 // 24 segments is not (measured: 1.5 "no instruction" stalls per issue and a slower kernel).
 template <int U>
 CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, float dist[kNumRays],
-                      unsigned long long *stats) {
+                      unsigned long long *stats, const WarpSeg *ws = nullptr) {
     const float R0 = 1.0e-3f;           // 1/1000: "no hit" (lib/car_env.py:198)
     float Rp[6], Rm[6], gq[6], gu;
-    if (U > 1) {
+    if (U == kWarpPerEnv) {
+#if defined(__CUDA_ARCH__)
+        cast_walls_warp(s, T, *ws, Rp, Rm, gq, gu);
+#else
+        (void)ws; gu = 0.0f;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) { Rp[l] = R0; Rm[l] = -R0; gq[l] = 0.0f; }
+#endif
+    } else if (U > 1) {
         WallAcc2 w;
         w.phx = (float)s.px; w.phy = (float)s.py;
 #pragma unroll
@@ -510,7 +570,7 @@ CE_HD void pose_observation(const EnvState &s, float vx10, float vy10, const flo
 // ---- one CarEnv.step with same-step autoreset --------------------------------------------------
 template <int U>
 CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackParams &P, const Tables &T,
-                    StepResult &o, unsigned long long *stats) {
+                    StepResult &o, unsigned long long *stats, const WarpSeg *ws = nullptr) {
     int thrust, turn;
     decode_action(action, thrust, turn);
     double reward = thrust > 0 ? 0.01 : 0.0;
@@ -529,7 +589,7 @@ CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackPar
     integrate(s, thrust, k_pre, T);
 
     float dist[kNumRays];
-    bool destroyed = cast_walls<U>(s, P, T, dist, stats);
+    bool destroyed = cast_walls<U>(s, P, T, dist, stats, ws);
     destroyed = destroyed || (P.start_destroyed != 0);
     s.t += 1;
     o.terminated = 0; o.truncated = 0;

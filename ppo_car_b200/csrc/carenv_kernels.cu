@@ -54,6 +54,7 @@ struct Handle {
     int smem_pad;             // tuning hook: extra dynamic shared memory per block (limits resident blocks per SM)
     int tc_tiles;             // tuning hook: 128-env groups per CTA of k_policy_rollout_tc (0 = chosen per launch)
     int pose_rows;            // fused rollout kernels: obs_buf holds 32-byte pose records instead of observations
+    int warp_per_env;         // 0 = warp-per-environment kernel for small batches, 1 = always, -1 = never
 };
 
 struct DeviceGuard {
@@ -73,6 +74,7 @@ struct DeviceGuard {
 #define CARENV_BLOCK 128
 #endif
 constexpr int kBlock = CARENV_BLOCK;
+constexpr int kWarpPerEnvMax = 2048;   // n_envs up to which k_rollout_warp is launched (tracks with <= 32 segments)
 
 template <typename FlagT> __device__ __forceinline__ FlagT make_flag(int v);
 template <> __device__ __forceinline__ uint8_t make_flag<uint8_t>(int v) { return (uint8_t)v; }
@@ -198,6 +200,64 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
     pos[e] = make_double2(s.px, s.py);
     vel[e] = make_double2(s.vx, s.vy);
     ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+}
+
+// Small batches: one WARP per environment, lane j = wall segment j (tracks with at most 32 segments), per-ray
+// extrema by warp-level integer REDUX (carenv_core.cuh: cast_walls_warp).  A lone thread-per-environment warp
+// needs ~1.9 us per step (1,700 dependent-ish instructions); here the 24 segments are evaluated side by side
+// and a step is ~600 warp-instructions.  Every lane carries the (identical) environment state and runs the scalar
+// part of the step redundantly; lane 0 writes the outputs.  Bit-identical to k_rollout.
+template <typename ActT, typename FlagT>
+__global__ void __launch_bounds__(128)
+k_rollout_warp(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int n_steps, double2 *__restrict__ pos,
+               double2 *__restrict__ vel, int4 *__restrict__ ints, const ActT *__restrict__ actions,
+               double reward_scale, float *__restrict__ obs_out, float *__restrict__ rew_out,
+               FlagT *__restrict__ term_out, FlagT *__restrict__ trunc_out, int4 *__restrict__ info_out,
+               unsigned long long *stats, int obs_mode) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= n_envs) return;
+
+    WarpSeg ws;
+    ws.active = lane < P.n_seg;
+    ws.f = G.segf[ws.active ? lane : 0];
+    ws.g = G.segd[ws.active ? lane : 0];
+    EnvState s;
+    {
+        const double2 p = pos[e], v = vel[e];
+        const int4 q = ints[e];
+        s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
+        s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
+    }
+    unsigned long long *my_stats = lane == 0 ? stats : nullptr;
+    int a_next = (int)actions[e];
+    for (int t = 0; t < n_steps; ++t) {
+        const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+        const int a = a_next;
+        if (t + 1 < n_steps) a_next = (int)actions[idx + (size_t)n_envs];
+        StepResult o;
+        env_step<kWarpPerEnv>(s, a, reward_scale, P, T, o, my_stats, &ws);
+        if (lane == 0) {
+            if (obs_mode == kObsFull) {
+                float2 *dst = reinterpret_cast<float2 *>(obs_out + idx * kObsDim);
+#pragma unroll
+                for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(o.obs[2 * i], o.obs[2 * i + 1]);
+            } else if (obs_mode == kObsPose) {
+                store_pose(reinterpret_cast<PoseRec *>(obs_out) + idx, s, o.obs[2], o.obs[3]);
+            }
+            rew_out[idx] = o.reward;
+            term_out[idx] = make_flag<FlagT>(o.terminated);
+            trunc_out[idx] = make_flag<FlagT>(o.truncated);
+            if (info_out) info_out[idx] = make_int4(o.gates_passed, o.time_passed, o.next_gate, o.gate_hit | (o.lap << 1));
+        }
+    }
+    if (lane == 0) {
+        pos[e] = make_double2(s.px, s.py);
+        vel[e] = make_double2(s.vx, s.vy);
+        ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+    }
 }
 
 // tcgen05 bring-up / unit test: D[128,256] = A[128,24] * B[256,24]^T with kind::tf32, accumulators in TMEM.
@@ -696,6 +756,19 @@ template <typename ActT, typename FlagT>
 int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints, const void *actions,
                    double reward_scale, float *obs_out, float *reward_out, void *term_out, void *trunc_out,
                    int32_t *info_out, cudaStream_t stream, int obs_mode) {
+    // small batches on small tracks: one warp per environment (crossover measured by benchmarks/small_batch.py)
+    const bool warp_ok = h->host.P.n_seg <= 32 && !h->force_generic;
+    if (warp_ok && (h->warp_per_env == 1 || (h->warp_per_env == 0 && n_envs <= kWarpPerEnvMax))) {
+        auto kern = k_rollout_warp<ActT, FlagT>;
+        const int grid = (n_envs + 3) / 4;
+        kern<<<grid, 128, h->smem_bytes, stream>>>(
+            h->host.P, h->dev, n_envs, n_steps, reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel),
+            reinterpret_cast<int4 *>(ints), static_cast<const ActT *>(actions), reward_scale, obs_out, reward_out,
+            static_cast<FlagT *>(term_out), static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out),
+            h->d_stats, obs_mode);
+        CU(cudaGetLastError());
+        return 0;
+    }
     int U = h->force_generic ? 1 : h->host.P.unroll;
     if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
     if (h->host.P.n_seg > kMaxSeg) U = 0;                   // geometry from shared memory
@@ -757,7 +830,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0; h->warp_per_env = 0;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -996,6 +1069,7 @@ int carenv_set_option(void *handle, const char *name, int value) {
         h->block = value; return 0;
     }
     if (std::string(name) == "pose_rows") { h->pose_rows = value ? 1 : 0; return 0; }
+    if (std::string(name) == "warp_per_env") { h->warp_per_env = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
     if (std::string(name) == "tc_tiles") {
         if (value != 0 && value != 2 && value != 4) return fail(CARENV_E_INVAL, "tc_tiles must be 0, 2 or 4");
         h->tc_tiles = value; return 0;

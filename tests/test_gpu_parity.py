@@ -452,3 +452,34 @@ def test_reset_with_track_path_switches_the_track_mid_run(golden_dir, tracks_dir
                trunc=g["lap_trunc"], gates_passed=g["lap_gates_passed"], time_passed=g["lap_time_passed"],
                next_gate_index=g["lap_next_gate_index"])
     assert_trajectory_matches(_gpu_traj(out), ref, what="big_track/lap after a track switch")
+
+
+@pytest.mark.parametrize("name", ["track", "big_track"])
+def test_warp_per_env_kernel_is_bit_identical_to_thread_per_env(golden_dir, tracks_dir, name):
+    """Small batches run k_rollout_warp (one warp per environment, lane = wall segment, REDUX extrema); forcing
+    either kernel gives the same bits — random rollouts, the lap trajectory of the golden file, pose records."""
+    path = os.path.join(tracks_dir, name + ".json")
+    n, T = 301, 700
+    rng = np.random.default_rng(8)
+    acts = torch.from_numpy(rng.choice(9, size=(T, n), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04]).astype(np.uint8)).cuda()
+    lap = torch.from_numpy(np.load(os.path.join(golden_dir, f"carenv_{name}.npz"))["lap_actions"]).cuda()
+    outs = {}
+    for mode in (1, -1):
+        env = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1)
+        env.set_option("warp_per_env", mode)
+        env.reset()
+        out = env.rollout(acts, store_info=True)
+        poses = env.rollout(acts[:50], store_poses=True)["poses"]
+        env2 = ppo_car_b200.VecCarEnv(lap.shape[1], path)
+        env2.set_option("warp_per_env", mode)
+        env2.reset()
+        out_lap = env2.rollout(lap, store_info=True)
+        outs[mode] = (out, poses, env.pos.clone(), env.ints.clone(), out_lap, env.slow_path_counts())
+    a, b = outs[1], outs[-1]
+    for k in ("obs", "reward", "terminated", "truncated"):
+        assert torch.equal(a[0][k], b[0][k]) and torch.equal(a[4][k], b[4][k]), k
+    for k in ("gates_passed", "time_passed", "next_gate_index", "events"):
+        assert torch.equal(a[0]["info"][k], b[0]["info"][k]) and torch.equal(a[4]["info"][k], b[4]["info"][k]), k
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert a[5] == b[5]                                       # the float64 fallback ran equally often
+    assert int(a[0]["terminated"].sum()) > n and int(((a[4]["info"]["events"] >> 1) & 1).sum()) == 1

@@ -106,7 +106,9 @@ int carenv_observe(void *handle, long long n, const void *poses, const long long
 /* Options.  "pose_rows" = 1: the fused rollout kernels below write 32-byte pose records (see
  * carenv_rollout_poses) through their obs_buf argument instead of observations.  Tuning / test hooks:
  * "force_generic" = 1 runs the generic segment loop even for tracks that have an unrolled kernel instantiation
- * (identical results); "max_unroll", "block", "smem_pad", "tc_tiles" select kernel variants for measurements. */
+ * (identical results); "warp_per_env" = 1 / -1 forces / forbids the warp-per-environment kernel that small
+ * batches (at most 2,048 environments, at most 32 wall segments) run by default (identical results);
+ * "max_unroll", "block", "smem_pad", "tc_tiles" select kernel variants for measurements. */
 int carenv_set_option(void *handle, const char *name, int value);
 
 /* Slow-path counters since the last reset of the counters: [0] lines re-evaluated in float64

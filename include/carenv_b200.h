@@ -136,6 +136,12 @@ int gae_reverse_scan(const float *rew, const float *val, const float *term, cons
  *   last_val [n] or NULL  critic value of the final observation (bootstrap for GAE, train.py:200)
  *   u_dbg [n_steps][n_envs] or NULL  the uniforms that were used (tests) */
 int carenv_policy_weights_floats(void);
+/* Pack the reference network's parameters (device pointers, nn.Linear layout weight[out][in], lib/model.py:10-26:
+ * actor 18-256-9, critic 18-256-1) into packed_out: carenv_policy_weights_floats() floats for
+ * carenv_policy_rollout (tensor_cores = 0) or carenv_policy_weights_floats_tc() for carenv_policy_rollout_tc. */
+int carenv_pack_policy(int tensor_cores, const float *w1_actor, const float *b1_actor, const float *w2_actor,
+                       const float *b2_actor, const float *w1_critic, const float *b1_critic, const float *w2_critic,
+                       const float *b2_critic, float *packed_out, void *stream);
 int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs, int n_steps, int env_offset,
                           unsigned long long seed, unsigned long long step0, double *pos, double *vel, int32_t *ints,
                           float *cur_obs, float *cur_term, float *cur_trunc, double reward_scale, float *obs_buf,

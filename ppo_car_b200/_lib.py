@@ -73,6 +73,8 @@ def lib():
     L.carenv_bench_ffma.argtypes = [i32, i32, vp, vp]
     L.carenv_tc_gemm_test.argtypes = [vp, vp, vp, vp]
     L.carenv_tc_gemm_test.restype = i32
+    L.carenv_pack_policy.argtypes = [i32] + [vp] * 10
+    L.carenv_pack_policy.restype = i32
     L.carenv_policy_weights_floats.restype = i32
     L.carenv_policy_rollout.argtypes = [vp, vp, i32, i32, i32, C.c_ulonglong, C.c_ulonglong, vp, vp, vp, vp, vp, vp,
                                         f64] + [vp] * 10

@@ -409,6 +409,61 @@ constexpr int kTcW2cOff = kTcW2Off + kHidden * 10;           // W2 actor as [j][
 constexpr int kTcTailOff = kTcW2cOff + kHidden;              // b2[0..9], b2c, pad
 constexpr int kTcWeightFloats = kTcTailOff + 12;             // 27,404 floats
 
+// Packing of the reference network's parameters (nn.Linear layout: weight [out][in], lib/model.py:10-26) into the
+// two layouts above, one thread per packed float: runs after every optimiser epoch, so it is one launch and not
+// forty small tensor operations (13 ms per epoch in PyTorch, as much as the rollout of 32,768 envs x 1,024 steps).
+template <bool TC>
+__global__ void __launch_bounds__(256)
+k_pack_policy(const float *__restrict__ w1a, const float *__restrict__ b1a, const float *__restrict__ w2a,
+              const float *__restrict__ b2a, const float *__restrict__ w1c, const float *__restrict__ b1c,
+              const float *__restrict__ w2c, const float *__restrict__ b2c, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float v = 0.0f;
+    if (TC) {
+        if (i >= kTcWeightFloats) return;
+        if (i < 4 * kTcBFloats) {                            // [actor hi | actor lo | critic hi | critic lo], UMMA layout
+            const int which = i / kTcBFloats, r = i % kTcBFloats;
+            const int j = (r / 192) * 8 + (r % 32) / 4, k = ((r % 192) / 32) * 4 + r % 4;
+            const float *w1 = which < 2 ? w1a : w1c, *b1 = which < 2 ? b1a : b1c;
+            const float x = k < kObsDim ? w1[j * kObsDim + k] : (k == kObsDim ? b1[j] : 0.0f);
+            const float hi = tc::to_tf32(x);
+            v = (which & 1) ? tc::to_tf32(x - hi) : hi;
+        } else if (i < kTcW2cOff) {                          // actor second layer as [j][10] (q = 9 is padding)
+            const int r = i - kTcW2Off, j = r / 10, q = r % 10;
+            v = q < kActions ? w2a[q * kHidden + j] : 0.0f;
+        } else if (i < kTcTailOff) {
+            v = w2c[i - kTcW2cOff];
+        } else {
+            const int r = i - kTcTailOff;                    // b2[0..8], 0, b2c, 0
+            v = r < kActions ? b2a[r] : (r == 10 ? b2c[0] : 0.0f);
+        }
+    } else {
+        if (i >= kPolicyFloats) return;
+        constexpr int kBody = (kHidden / 2) * kPairFloats;
+        if (i < kBody) {
+            const int p = i / kPairFloats, r = i % kPairFloats;   // pair of hidden units (2p, 2p + 1)
+            const bool critic = r >= kActorPairFloats;
+            const int c = critic ? r - kActorPairFloats : r;
+            const float *w1 = critic ? w1c : w1a, *b1 = critic ? b1c : b1a;
+            if (c < 36) v = w1[(2 * p + (c & 1)) * kObsDim + (c >> 1)];
+            else if (c < 38) v = b1[2 * p + (c - 36)];
+            else if (c >= 40) {
+                const int d = c - 40;
+                if (!critic) {                               // (W2[2q][j], W2[2q+1][j]) for j = 2p, 2p + 1
+                    const int q = d >> 2, sft = (d >> 1) & 1, rr = d & 1, row = 2 * q + rr;
+                    v = row < kActions ? w2a[row * kHidden + 2 * p + sft] : 0.0f;
+                } else if (d < 2) {
+                    v = w2c[2 * p + d];
+                }
+            }
+        } else {
+            const int r = i - kBody;
+            v = r < kActions ? b2a[r] : (r == 10 ? b2c[0] : 0.0f);
+        }
+    }
+    out[i] = v;
+}
+
 template <int U, int TILES>
 __global__ void __launch_bounds__(TILES * 128 + 32, 1)
 k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const float *__restrict__ weights,
@@ -957,6 +1012,22 @@ int carenv_observe(void *handle, long long n, const void *poses, const long long
     if (U == 2) return launch(k_observe<2>);
     if (U == 0) return launch(k_observe<0>);
     return launch(k_observe<1>);
+}
+
+int carenv_pack_policy(int tensor_cores, const float *w1a, const float *b1a, const float *w2a, const float *b2a,
+                       const float *w1c, const float *b1c, const float *w2c, const float *b2c, float *packed_out,
+                       void *stream) {
+    if (!w1a || !b1a || !w2a || !b2a || !w1c || !b1c || !w2c || !b2c || !packed_out)
+        return fail(CARENV_E_INVAL, "null pointer");
+    const int n = tensor_cores ? kTcWeightFloats : kPolicyFloats;
+    if (tensor_cores)
+        k_pack_policy<true><<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w1a, b1a, w2a, b2a, w1c, b1c,
+                                                                                           w2c, b2c, packed_out);
+    else
+        k_pack_policy<false><<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w1a, b1a, w2a, b2a, w1c, b1c,
+                                                                                            w2c, b2c, packed_out);
+    CU(cudaGetLastError());
+    return 0;
 }
 
 int carenv_policy_weights_floats(void) { return kPolicyFloats; }

@@ -14,6 +14,25 @@ from . import _lib
 HIDDEN, OBS, ACTIONS = 256, 18, 9
 
 
+def _pack_on_device(tensor_cores: bool, actor, critic, out):
+    """One launch of k_pack_policy (C ABI carenv_pack_policy) for parameters that live on a CUDA device."""
+    L = _lib.lib()
+    params = [actor[0].weight, actor[0].bias, actor[2].weight, actor[2].bias,
+              critic[0].weight, critic[0].bias, critic[2].weight, critic[2].bias]
+    params = [p.detach().float().contiguous() for p in params]
+    n = L.carenv_policy_weights_floats_tc() if tensor_cores else L.carenv_policy_weights_floats()
+    dev = params[0].device
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+    elif out.numel() != n or out.dtype != torch.float32 or out.device != dev or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float32 tensor of {n} elements on {dev}")
+    with torch.cuda.device(dev):
+        rc = L.carenv_pack_policy(int(tensor_cores), *[C.c_void_p(p.data_ptr()) for p in params],
+                                  C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "carenv_pack_policy")
+    return out
+
+
 def pack_policy_weights(actor, critic, out: torch.Tensor | None = None) -> torch.Tensor:
     """Lay the four Linear layers out the way policy_core.cuh reads them: per pair of hidden units
     (j, j+1) an actor block [18 x (W1[j,k], W1[j+1,k]) | b1 pair, pad | 5 x (W2[2q,j], W2[2q+1,j],
@@ -24,6 +43,8 @@ def pack_policy_weights(actor, critic, out: torch.Tensor | None = None) -> torch
     w1c, b1c, w2c, b2c = critic[0].weight, critic[0].bias, critic[2].weight, critic[2].bias
     if tuple(w1a.shape) != (HIDDEN, OBS) or tuple(w2a.shape) != (ACTIONS, HIDDEN) or tuple(w2c.shape) != (1, HIDDEN):
         raise ValueError("fused rollout supports the reference network only: 18-256-9 actor, 18-256-1 critic")
+    if w1a.is_cuda:                                         # one kernel launch; the code below documents the layout
+        return _pack_on_device(False, actor, critic, out)
     dev, P = w1a.device, HIDDEN // 2
     with torch.no_grad():
         z2 = torch.zeros((P, 2), device=dev)
@@ -57,6 +78,8 @@ def pack_policy_weights_tc(actor, critic, out: torch.Tensor | None = None) -> to
     w1c, b1c, w2c, b2c = critic[0].weight, critic[0].bias, critic[2].weight, critic[2].bias
     if tuple(w1a.shape) != (HIDDEN, OBS) or tuple(w2a.shape) != (ACTIONS, HIDDEN) or tuple(w2c.shape) != (1, HIDDEN):
         raise ValueError("fused rollout supports the reference network only: 18-256-9 actor, 18-256-1 critic")
+    if w1a.is_cuda:                                         # one kernel launch; the code below documents the layout
+        return _pack_on_device(True, actor, critic, out)
     dev = w1a.device
     with torch.no_grad():
         j = torch.arange(HIDDEN, device=dev).view(-1, 1)

@@ -174,3 +174,22 @@ def test_training_with_pose_rows_and_graph_update():
     hist = train(args)
     assert all(math.isfinite(h["total_loss"]) for h in hist)
     assert hist[-1]["avg_reward"] > hist[0]["avg_reward"] + 0.03
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_device_packing_kernel_equals_the_torch_layout_code(tensor_cores):
+    """carenv_pack_policy (one launch) against the PyTorch statement of the same layout evaluated on the CPU."""
+    torch.manual_seed(13)
+    net = ActorCritic(18, 9)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn_like(p) * 0.3)                # biases are zero after the reference's init
+    pack = ppo_car_b200.pack_policy_weights_tc if tensor_cores else ppo_car_b200.pack_policy_weights
+    ref = pack(net.actor, net.critic)                        # CPU tensors: the torch code path
+    net_gpu = ActorCritic(18, 9).cuda()
+    net_gpu.load_state_dict(net.state_dict())
+    got = pack(net_gpu.actor, net_gpu.critic)
+    assert got.is_cuda and torch.equal(got.cpu(), ref)
+    out = torch.empty_like(got)
+    assert pack(net_gpu.actor, net_gpu.critic, out=out) is out and torch.equal(out, got)

@@ -159,6 +159,30 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
                              float *obs_buf, float *act_buf, float *rew_buf, float *val_buf, float *term_buf,
                              float *trunc_buf, float *logp_buf, float *last_val, float *u_dbg, void *stream);
 
+/* One PPO minibatch update of the reference network (train.py:223-261: clipped surrogate, 0.5-weighted value
+ * loss, entropy bonus, advantage normalised per minibatch with the unbiased std clamped at 1e-5,
+ * clip_grad_norm_, Adam) in three launches instead of an autograd graph of ~60 kernels.  All pointers are
+ * device pointers; parameters in nn.Linear layout (lib/model.py:10-26).
+ *   carenv_ppo_grad   gradients of the minibatch `idx` [batch] (rows of obs [.][18] — or obs already gathered
+ *                     [batch][18] if obs_is_gathered — and of the flat act / old_logp / adv / ret arrays) into
+ *                     grads [carenv_ppo_num_params()] in the order W1a b1a W2a b2a W1c b1c W2c b2c; deterministic.
+ *   carenv_ppo_adam   grads *= grad_scale (1 / world size after an all-reduce), global-norm clip, Adam step
+ *                     (exp_avg / exp_avg_sq [num_params], *step incremented, learning rate read from *lr),
+ *                     sums4 += (policy loss, value loss, entropy, total loss) of the minibatch.
+ *   scratch           carenv_ppo_scratch_floats(batch) floats, written by _grad and read by _adam. */
+int carenv_ppo_num_params(void);
+int carenv_ppo_scratch_floats(int batch);
+int carenv_ppo_grad(const float *w1_actor, const float *b1_actor, const float *w2_actor, const float *b2_actor,
+                    const float *w1_critic, const float *b1_critic, const float *w2_critic, const float *b2_critic,
+                    const float *obs, int obs_is_gathered, const long long *idx, const float *act,
+                    const float *old_logp, const float *adv, const float *ret, int batch, double clip_ratio,
+                    double vf_coef, double ent_coef, float *scratch, float *grads, void *stream);
+int carenv_ppo_adam(float *w1_actor, float *b1_actor, float *w2_actor, float *b2_actor, float *w1_critic,
+                    float *b1_critic, float *w2_critic, float *b2_critic, float *grads, double grad_scale,
+                    float *exp_avg, float *exp_avg_sq, const float *lr, int *step, double beta1, double beta2,
+                    double eps, double max_grad_norm, const float *scratch, int batch, double vf_coef,
+                    double ent_coef, float *sums4, void *stream);
+
 /* Test hook for the tensor-core building blocks (csrc/tc_mlp.cuh): D[128][256] = A[128][24] * B[256][24]^T,
  * tcgen05.mma kind::tf32 with the accumulator in tensor memory; device pointers, row-major float32. */
 int carenv_tc_gemm_test(const float *A, const float *B, float *D, void *stream);

@@ -14,7 +14,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("CARENV_LIB") or os.path.join(_PKG, "libcarenv_b200.so")   # override: kernel experiments
 SOURCES = [os.path.join(_PKG, "csrc", f)
-           for f in ("carenv_kernels.cu", "carenv_core.cuh", "carenv_tables.h", "policy_core.cuh", "tc_mlp.cuh")]
+           for f in ("carenv_kernels.cu", "carenv_core.cuh", "carenv_tables.h", "policy_core.cuh", "tc_mlp.cuh",
+                     "ppo_update.cuh")]
 HEADER = os.path.join(ROOT, "include", "carenv_b200.h")
 
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
@@ -73,6 +74,13 @@ def lib():
     L.carenv_bench_ffma.argtypes = [i32, i32, vp, vp]
     L.carenv_tc_gemm_test.argtypes = [vp, vp, vp, vp]
     L.carenv_tc_gemm_test.restype = i32
+    L.carenv_ppo_num_params.restype = i32
+    L.carenv_ppo_scratch_floats.argtypes = [i32]
+    L.carenv_ppo_scratch_floats.restype = i32
+    L.carenv_ppo_grad.argtypes = [vp] * 8 + [vp, i32, vp, vp, vp, vp, vp, i32, f64, f64, f64, vp, vp, vp]
+    L.carenv_ppo_grad.restype = i32
+    L.carenv_ppo_adam.argtypes = [vp] * 8 + [vp, f64, vp, vp, vp, vp, f64, f64, f64, f64, vp, i32, f64, f64, vp, vp]
+    L.carenv_ppo_adam.restype = i32
     L.carenv_pack_policy.argtypes = [i32] + [vp] * 10
     L.carenv_pack_policy.restype = i32
     L.carenv_policy_weights_floats.restype = i32

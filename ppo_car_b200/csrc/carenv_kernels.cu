@@ -19,6 +19,7 @@
 #include "../../include/carenv_b200.h"
 #include "carenv_tables.h"
 #include "policy_core.cuh"
+#include "ppo_update.cuh"
 #include "tc_mlp.cuh"
 
 using namespace carenv;
@@ -1026,6 +1027,51 @@ int carenv_pack_policy(int tensor_cores, const float *w1a, const float *b1a, con
     else
         k_pack_policy<false><<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w1a, b1a, w2a, b2a, w1c, b1c,
                                                                                             w2c, b2c, packed_out);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int carenv_ppo_num_params(void) { return ppo::kNumParams; }
+int carenv_ppo_scratch_floats(int batch) { return batch > 0 && batch <= ppo::kMaxBatch ? ppo::scratch_floats(batch) : -1; }
+
+int carenv_ppo_grad(const float *w1a, const float *b1a, const float *w2a, const float *b2a, const float *w1c,
+                    const float *b1c, const float *w2c, const float *b2c, const float *obs, int obs_is_gathered,
+                    const long long *idx, const float *act, const float *old_logp, const float *adv, const float *ret,
+                    int batch, double clip_ratio, double vf_coef, double ent_coef, float *scratch, float *grads,
+                    void *stream) {
+    if (batch < 2 || batch > ppo::kMaxBatch) return fail(CARENV_E_INVAL, "batch must be in 2..1024");
+    if (!w1a || !b1a || !w2a || !b2a || !w1c || !b1c || !w2c || !b2c || !obs || !idx || !act || !old_logp || !adv ||
+        !ret || !scratch || !grads)
+        return fail(CARENV_E_INVAL, "null pointer");
+    const ppo::Params P{w1a, b1a, w2a, b2a, w1c, b1c, w2c, b2c};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nb = (batch + ppo::kFwdThreads - 1) / ppo::kFwdThreads;
+    const size_t smem_f = sizeof(float) * (ppo::kH * 20 + ppo::kH * ppo::kDz + 4);
+    ppo::k_ppo_forward<<<dim3(nb, 2), ppo::kFwdThreads, smem_f, st>>>(P, obs, obs_is_gathered, idx, act, old_logp, adv,
+                                                                      ret, batch, (float)clip_ratio, (float)vf_coef,
+                                                                      (float)ent_coef, scratch);
+    CU(cudaGetLastError());
+    const size_t smem_b = sizeof(float) * ((size_t)batch * (20 + ppo::kDz) +
+                                           (size_t)ppo::kBwdSlices * ppo::kBwdUnits * (ppo::kIn + 1 + ppo::kQ + 1));
+    CU(cudaFuncSetAttribute(ppo::k_ppo_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    ppo::k_ppo_backward<<<dim3(ppo::kH / ppo::kBwdUnits, 2), ppo::kBwdUnits * ppo::kBwdSlices, smem_b, st>>>(P, batch,
+                                                                                                          scratch, grads);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int carenv_ppo_adam(float *w1a, float *b1a, float *w2a, float *b2a, float *w1c, float *b1c, float *w2c, float *b2c,
+                    float *grads, double grad_scale, float *exp_avg, float *exp_avg_sq, const float *lr, int *step,
+                    double beta1, double beta2, double eps, double max_grad_norm, const float *scratch, int batch,
+                    double vf_coef, double ent_coef, float *sums4, void *stream) {
+    if (batch < 2 || batch > ppo::kMaxBatch) return fail(CARENV_E_INVAL, "batch must be in 2..1024");
+    if (!w1a || !b1a || !w2a || !b2a || !w1c || !b1c || !w2c || !b2c || !grads || !exp_avg || !exp_avg_sq || !lr ||
+        !step || !scratch || !sums4)
+        return fail(CARENV_E_INVAL, "null pointer");
+    const ppo::MutableParams P{w1a, b1a, w2a, b2a, w1c, b1c, w2c, b2c};
+    ppo::k_ppo_adam<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+        P, grads, (float)grad_scale, exp_avg, exp_avg_sq, lr, step, (float)beta1, (float)beta2, (float)eps,
+        (float)max_grad_norm, scratch, batch, (float)vf_coef, (float)ent_coef, sums4);
     CU(cudaGetLastError());
     return 0;
 }

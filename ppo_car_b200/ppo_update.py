@@ -1,0 +1,69 @@
+"""Fused PPO minibatch update (C ABI carenv_ppo_grad / carenv_ppo_adam, csrc/ppo_update.cuh).
+
+Restates train.py:223-261 for the reference network (lib/model.py:10-26): clipped surrogate, value loss,
+entropy bonus, per-minibatch advantage normalisation, clip_grad_norm_, Adam — three kernel launches per
+minibatch (plus one NCCL all-reduce of the 12,298 gradients when there are several ranks) instead of an
+autograd graph of about sixty.  The parameters stay ordinary ``nn.Parameter`` tensors and are updated in place.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class FusedPPOUpdate:
+    def __init__(self, actor, critic, batch_size: int, lr: float, clip_ratio: float = 0.2, vf_coef: float = 0.5,
+                 ent_coef: float = 0.001, max_grad_norm: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-5):
+        self.L = _lib.lib()
+        self.params = [actor[0].weight, actor[0].bias, actor[2].weight, actor[2].bias,
+                       critic[0].weight, critic[0].bias, critic[2].weight, critic[2].bias]
+        shapes = [tuple(p.shape) for p in self.params]
+        if shapes != [(256, 18), (256,), (9, 256), (9,), (256, 18), (256,), (1, 256), (1,)]:
+            raise ValueError("the fused update supports the reference network only: 18-256-9 actor, 18-256-1 critic")
+        dev = self.params[0].device
+        if dev.type != "cuda" or any(p.dtype != torch.float32 or not p.is_contiguous() for p in self.params):
+            raise _lib.CarEnvError("parameters must be contiguous float32 CUDA tensors")
+        n = self.L.carenv_ppo_num_params()
+        scratch = self.L.carenv_ppo_scratch_floats(int(batch_size))
+        if scratch < 0:
+            raise ValueError("batch_size must be in 2..1024")
+        self.device, self.batch = dev, int(batch_size)
+        self.grads = torch.zeros(n, device=dev)
+        self.exp_avg, self.exp_avg_sq = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        self.scratch = torch.zeros(scratch, device=dev)
+        self.lr = torch.tensor([lr], dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sums = torch.zeros(4, device=dev)                  # policy loss, value loss, entropy, total loss
+        self.clip_ratio, self.vf_coef, self.ent_coef, self.max_grad_norm = clip_ratio, vf_coef, ent_coef, max_grad_norm
+        self.betas, self.eps = betas, eps
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def grad(self, obs, idx, act, old_logp, adv, ret, obs_is_gathered: bool = False):
+        """Gradients of one minibatch into ``self.grads``.  ``idx`` [batch] int64 indexes the flat arrays."""
+        with torch.cuda.device(self.device):
+            rc = self.L.carenv_ppo_grad(*[_p(p) for p in self.params], _p(obs), int(obs_is_gathered), _p(idx), _p(act),
+                                        _p(old_logp), _p(adv), _p(ret), self.batch, self.clip_ratio, self.vf_coef,
+                                        self.ent_coef, _p(self.scratch), _p(self.grads), self._stream())
+        _lib.check(rc, "carenv_ppo_grad")
+        return self.grads
+
+    def apply(self, world: int = 1):
+        """(All-reduce,) clip, Adam step, statistics."""
+        if world > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+        with torch.cuda.device(self.device):
+            rc = self.L.carenv_ppo_adam(*[_p(p) for p in self.params], _p(self.grads), 1.0 / world, _p(self.exp_avg),
+                                        _p(self.exp_avg_sq), _p(self.lr), _p(self.step_count), self.betas[0],
+                                        self.betas[1], self.eps, self.max_grad_norm, _p(self.scratch), self.batch,
+                                        self.vf_coef, self.ent_coef, _p(self.sums), self._stream())
+        _lib.check(rc, "carenv_ppo_adam")

@@ -91,6 +91,9 @@ def parse_args(argv=None):
                         "per epoch (carenv_policy_rollout); needs the reference network shape")
     p.add_argument("--fused-cuda-cores", action="store_true",
                    help="with --fused-rollout: use the CUDA-core kernel instead of the tensor-core one")
+    p.add_argument("--fused-update", action="store_true",
+                   help="one minibatch update = three kernel launches (carenv_ppo_grad / carenv_ppo_adam: forward, "
+                        "loss, backward, clip, Adam for the reference network) instead of a PyTorch autograd graph")
     p.add_argument("--compact-obs", action="store_true",
                    help="with --fused-rollout: store 32-byte pose records instead of observations and recompute the "
                         "minibatch observations in the update (VecCarEnv.observe)")
@@ -122,6 +125,12 @@ def train(args) -> list[dict]:
     obs_dim = envs.single_observation_space.shape
     agent = ActorCritic(obs_dim[0], envs.single_action_space.n).to(dev)
     graph_update = bool(args.graph_update)                 # with world > 1 the NCCL all-reduce is captured too
+    fused_upd = None
+    if args.fused_update:
+        from .ppo_update import FusedPPOUpdate
+
+        fused_upd = FusedPPOUpdate(agent.actor, agent.critic, args.batch_size, args.learning_rate, args.clip_ratio,
+                                   args.vf_coef, args.ent_coef, args.max_grad_norm)
     if graph_update:                                        # capturable Adam with the learning rate in a tensor
         opt = torch.optim.Adam(agent.parameters(), lr=torch.tensor(args.learning_rate, device=dev), eps=1e-5,
                                capturable=True)
@@ -214,6 +223,11 @@ def train(args) -> list[dict]:
                 """One minibatch: draw indices, clipped-surrogate loss, backward, (all-reduce), clip, Adam."""
                 torch.randint(0, T * n, (args.batch_size,), device=dev, out=idx_static)
                 idx = idx_static
+                if fused_upd is not None:
+                    obs_in = envs.observe(obs_f, idx) if args.compact_obs else obs_f
+                    fused_upd.grad(obs_in, idx, act_f, logp_f, adv_f, ret_f, obs_is_gathered=args.compact_obs)
+                    fused_upd.apply(world)
+                    return
                 obs_mb = envs.observe(obs_f, idx) if args.compact_obs else obs_f[idx]
                 _, new_logp, ent, new_val = agent.act(obs_mb, act_f[idx])
                 ratio = torch.exp(new_logp - logp_f[idx])
@@ -250,12 +264,17 @@ def train(args) -> list[dict]:
                     update_step()
                 sums.zero_()
         sums.zero_()
+        if fused_upd is not None:
+            fused_upd.sums.zero_()
         for _ in range(args.train_iters * n_mb):
             if update_graph is not None:
                 update_graph.replay()
             else:
                 update_step()
-        if sched is not None:
+        if fused_upd is not None:
+            fused_upd.lr.mul_(args.learning_rate_decay)
+            sums.copy_(fused_upd.sums)
+        elif sched is not None:
             sched.step()
         else:
             opt.param_groups[0]["lr"].mul_(args.learning_rate_decay)
@@ -263,7 +282,7 @@ def train(args) -> list[dict]:
         s = (sums / args.train_iters).tolist()
         rec = {"epoch": epoch, "global_step": global_step, "avg_reward": rew_sum / steps / args.reward_scaling,
                "episodes": episodes, "policy_loss": s[0], "value_loss": s[1], "entropy": s[2], "total_loss": s[3],
-               "lr": float(opt.param_groups[0]["lr"]), "sps": global_step / (time.time() - t_start),
+               "lr": float(fused_upd.lr if fused_upd is not None else opt.param_groups[0]["lr"]), "sps": global_step / (time.time() - t_start),
                "wall_s": time.time() - t_start}
         history.append(rec)
         if rank == 0:

@@ -100,10 +100,11 @@ def test_many_adam_steps_track_torch_adam():
     assert int(upd.step_count) == 40
 
 
-@pytest.mark.parametrize("extra", [[], ["--graph-update"], ["--compact-obs", "--graph-update"]])
+@pytest.mark.parametrize("extra", [["--fused-rollout"], ["--fused-rollout", "--graph-update"],
+                                   ["--fused-rollout", "--compact-obs", "--graph-update"], ["--cuda-graph"]])
 def test_training_with_fused_update_improves_reward(extra):
     args = parse_args(["--track", "big_track", "--n-envs", "64", "--n-epochs", "12", "--n-steps", "256",
-                       "--fused-rollout", "--fused-update"] + extra)
+                       "--fused-update"] + extra)
     hist = train(args)
     assert all(math.isfinite(h["total_loss"]) for h in hist)
     assert hist[-1]["avg_reward"] > hist[0]["avg_reward"] + 0.03

@@ -27,6 +27,7 @@
 #ifndef CARENV_B200_H
 #define CARENV_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -82,6 +83,20 @@ int carenv_reset(void *handle, int n_envs, double *pos, double *vel, int32_t *in
 int carenv_step(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions,
                 int action_dtype, double reward_scale, float *obs_out, float *reward_out, void *term_out,
                 void *trunc_out, int flag_dtype, int32_t *info_out, void *stream);
+
+/* carenv_step with HOST buffers — what the reference's rollout loop does around envs.step (train.py:185-192:
+ * numpy actions in, numpy observations / rewards / flags out).  actions_host [n_envs] of action_dtype and the
+ * *_host outputs (layouts as in carenv_step; info_host may be NULL) are host pointers; pinned memory
+ * (carenv_host_alloc, or any cudaHostAlloc / torch pin_memory buffer) makes the copies asynchronous — the batch
+ * is cut into sub-ranges of about 65,536 environments on internal streams so that the device->host copy of one
+ * range overlaps the kernel and copies of the next.  The state arrays stay on the device.  The call is ordered
+ * after earlier work on `stream`, later work on `stream` sees the new state, and it RETURNS WHEN THE RESULTS ARE
+ * IN THE HOST BUFFERS.  The library owns the staging buffers (per handle, sized on first use). */
+int carenv_step_host(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions_host,
+                     int action_dtype, double reward_scale, float *obs_host, float *reward_host, void *term_host,
+                     void *trunc_host, int flag_dtype, int32_t *info_host, void *stream);
+int carenv_host_alloc(size_t bytes, void **ptr);   /* pinned host memory for the call above */
+int carenv_host_free(void *ptr);
 
 /* n_steps consecutive steps in ONE launch (the rollout loop of train.py:173-195 with the
  * actions given up front).  actions is [n_steps][n_envs]; every output is [n_steps][n_envs]...

@@ -13,6 +13,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <string>
 
@@ -56,7 +60,57 @@ struct Handle {
     int tc_tiles;             // tuning hook: 128-env groups per CTA of k_policy_rollout_tc (0 = chosen per launch)
     int pose_rows;            // fused rollout kernels: obs_buf holds 32-byte pose records instead of observations
     int warp_per_env;         // 0 = warp-per-environment kernel for small batches, 1 = always, -1 = never
+    struct HostStep *hs;      // staging buffers / streams of carenv_step_host (allocated on first use)
 };
+
+// Resources of the host-buffer step path (carenv_step_host): device staging for one step of `cap` environments,
+// a pinned byte buffer the caller's actions are narrowed into, side streams and events for the sub-range pipeline.
+struct HostStep {
+    static constexpr int kMaxRanges = 8;
+    int cap = 0, flag_bytes = 0;
+    unsigned char *d_act = nullptr, *h_act = nullptr;
+    float *d_obs = nullptr, *d_rew = nullptr;
+    unsigned char *d_term = nullptr, *d_trunc = nullptr;
+    int32_t *d_info = nullptr;
+    cudaStream_t streams[kMaxRanges] = {};
+    cudaEvent_t ready = nullptr, done[kMaxRanges] = {};
+    void release() {
+        cudaFree(d_act); cudaFreeHost(h_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc);
+        cudaFree(d_info);
+        for (int i = 0; i < kMaxRanges; ++i) {
+            if (streams[i]) cudaStreamDestroy(streams[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+        }
+        if (ready) cudaEventDestroy(ready);
+        *this = HostStep();
+    }
+};
+
+// int64 actions (what train.py:185 passes) -> one byte each; anything outside 0..8 acts like 8 (lib/car_env.py:698-722).
+// Runs on the host in front of every sub-range of carenv_step_host, so it is written for SSE2 (4 actions per
+// iteration, ~0.3 ns each) instead of a scalar 64-bit compare-and-select loop (1 ns each).
+static void narrow_actions_i64(const unsigned long long *a, unsigned char *d, int m) {
+    int i = 0;
+#if defined(__SSE2__)
+    const __m128i sign = _mm_set1_epi32((int)0x80000000u), eight = _mm_set1_epi32(8), zero = _mm_setzero_si128();
+    const __m128i eight_s = _mm_xor_si128(eight, sign);
+    for (; i + 4 <= m; i += 4) {
+        const __m128 x0 = _mm_castsi128_ps(_mm_loadu_si128(reinterpret_cast<const __m128i *>(a + i)));
+        const __m128 x1 = _mm_castsi128_ps(_mm_loadu_si128(reinterpret_cast<const __m128i *>(a + i + 2)));
+        const __m128i lo = _mm_castps_si128(_mm_shuffle_ps(x0, x1, 0x88));     // low halves of the four int64
+        const __m128i hi = _mm_castps_si128(_mm_shuffle_ps(x0, x1, 0xDD));     // high halves
+        const __m128i ok_hi = _mm_cmpeq_epi32(hi, zero);
+        const __m128i bad_lo = _mm_cmpgt_epi32(_mm_xor_si128(lo, sign), eight_s);  // unsigned lo > 8
+        const __m128i ok = _mm_andnot_si128(bad_lo, ok_hi);
+        __m128i v = _mm_or_si128(_mm_and_si128(ok, lo), _mm_andnot_si128(ok, eight));
+        v = _mm_packs_epi32(v, v);
+        v = _mm_packus_epi16(v, v);
+        const int w = _mm_cvtsi128_si32(v);
+        memcpy(d + i, &w, 4);
+    }
+#endif
+    for (; i < m; ++i) { const unsigned long long u = a[i]; d[i] = (unsigned char)(u < 8ull ? u : 8ull); }
+}
 
 struct DeviceGuard {
     int prev;
@@ -886,7 +940,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0; h->warp_per_env = 0;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0; h->warp_per_env = 0; h->hs = nullptr;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -936,6 +990,7 @@ int carenv_destroy(void *handle) {
         DeviceGuard guard(h->device);
         cudaFree(h->d_blob);
         cudaFree(h->d_stats);
+        if (h->hs) { h->hs->release(); delete h->hs; }
     }
     delete h;
     return 0;
@@ -987,6 +1042,96 @@ int carenv_rollout_poses(void *handle, int n_envs, int n_steps, double *pos, dou
     return dispatch_rollout(handle, n_envs, n_steps, pos, vel, ints, actions, action_dtype, reward_scale,
                             static_cast<float *>(pose_out), reward_out, term_out, trunc_out, flag_dtype, info_out,
                             stream, kObsPose);
+}
+
+int carenv_host_alloc(size_t bytes, void **ptr) {
+    if (!ptr) return fail(CARENV_E_INVAL, "null pointer");
+    *ptr = nullptr;
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+
+int carenv_host_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return 0;
+}
+
+int carenv_step_host(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions_host,
+                     int action_dtype, double reward_scale, float *obs_host, float *reward_host, void *term_host,
+                     void *trunc_host, int flag_dtype, int32_t *info_host, void *stream) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(CARENV_E_INVAL, "null handle");
+    if (n_envs < 0) return fail(CARENV_E_INVAL, "negative n_envs");
+    if (n_envs == 0) return 0;
+    if (!pos || !vel || !ints || !actions_host || !obs_host || !reward_host || !term_host || !trunc_host)
+        return fail(CARENV_E_INVAL, "null state / action / output pointer");
+    if (action_dtype != CARENV_ACT_U8 && action_dtype != CARENV_ACT_I32 && action_dtype != CARENV_ACT_I64)
+        return fail(CARENV_E_INVAL, "unknown action_dtype");
+    if (flag_dtype != CARENV_FLAG_U8 && flag_dtype != CARENV_FLAG_F32) return fail(CARENV_E_INVAL, "unknown flag_dtype");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    const int fb = flag_dtype == CARENV_FLAG_F32 ? 4 : 1;
+    if (!h->hs) h->hs = new HostStep();
+    HostStep &S = *h->hs;
+    if (S.cap < n_envs || S.flag_bytes != fb) {               // (re)allocate the staging for this batch size
+        S.release();
+        const size_t n = (size_t)n_envs;
+        cudaError_t e = cudaMalloc(&S.d_act, n);
+        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&S.h_act), n, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaMalloc(&S.d_obs, n * kObsDim * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&S.d_rew, n * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&S.d_term, n * fb);
+        if (e == cudaSuccess) e = cudaMalloc(&S.d_trunc, n * fb);
+        if (e == cudaSuccess) e = cudaMalloc(&S.d_info, n * 4 * sizeof(int32_t));
+        for (int i = 0; i < HostStep::kMaxRanges && e == cudaSuccess; ++i) {
+            e = cudaStreamCreateWithFlags(&S.streams[i], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.done[i], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.ready, cudaEventDisableTiming);
+        if (e != cudaSuccess) { S.release(); return cuda_fail(e, "carenv_step_host: staging allocation"); }
+        S.cap = n_envs; S.flag_bytes = fb;
+    }
+    // sub-ranges of about 65,536 environments (6 MB of results): the cast + H2D + kernel of range i + 1 overlap the
+    // D2H copy of range i, which is the bottleneck (94 B per environment over PCIe)
+    int n_ranges = n_envs / 65536;
+    n_ranges = n_ranges < 1 ? 1 : (n_ranges > HostStep::kMaxRanges ? HostStep::kMaxRanges : n_ranges);
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    CU(cudaEventRecord(S.ready, user));                       // earlier work on the caller's stream (reset, device steps)
+    for (int r = 0; r < n_ranges; ++r) {
+        const int lo = (int)((long long)n_envs * r / n_ranges), hi = (int)((long long)n_envs * (r + 1) / n_ranges);
+        const int m = hi - lo;
+        if (action_dtype == CARENV_ACT_I64) {
+            narrow_actions_i64(static_cast<const unsigned long long *>(actions_host) + lo, S.h_act + lo, m);
+        } else if (action_dtype == CARENV_ACT_I32) {
+            const uint32_t *a = static_cast<const uint32_t *>(actions_host) + lo;
+            unsigned char *d = S.h_act + lo;
+            for (int i = 0; i < m; ++i) { const uint32_t u = a[i]; d[i] = (unsigned char)(u < 8u ? u : 8u); }
+        } else {
+            memcpy(S.h_act + lo, static_cast<const unsigned char *>(actions_host) + lo, (size_t)m);
+        }
+        cudaStream_t st = S.streams[r];
+        CU(cudaStreamWaitEvent(st, S.ready, 0));
+        CU(cudaMemcpyAsync(S.d_act + lo, S.h_act + lo, (size_t)m, cudaMemcpyHostToDevice, st));
+        const int rc = dispatch_rollout(h, m, 1, pos + 2 * (size_t)lo, vel + 2 * (size_t)lo, ints + 4 * (size_t)lo,
+                                        S.d_act + lo, CARENV_ACT_U8, reward_scale, S.d_obs + (size_t)lo * kObsDim,
+                                        S.d_rew + lo, S.d_term + (size_t)lo * fb, S.d_trunc + (size_t)lo * fb, flag_dtype,
+                                        info_host ? S.d_info + 4 * (size_t)lo : nullptr, st, kObsFull);
+        if (rc != 0) return rc;
+        CU(cudaMemcpyAsync(obs_host + (size_t)lo * kObsDim, S.d_obs + (size_t)lo * kObsDim,
+                           (size_t)m * kObsDim * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(reward_host + lo, S.d_rew + lo, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(static_cast<unsigned char *>(term_host) + (size_t)lo * fb, S.d_term + (size_t)lo * fb,
+                           (size_t)m * fb, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(static_cast<unsigned char *>(trunc_host) + (size_t)lo * fb, S.d_trunc + (size_t)lo * fb,
+                           (size_t)m * fb, cudaMemcpyDeviceToHost, st));
+        if (info_host)
+            CU(cudaMemcpyAsync(info_host + 4 * (size_t)lo, S.d_info + 4 * (size_t)lo, (size_t)m * 4 * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(S.done[r], st));
+    }
+    for (int r = 0; r < n_ranges; ++r) CU(cudaStreamWaitEvent(user, S.done[r], 0));   // later device work sees the new state
+    for (int r = 0; r < n_ranges; ++r) CU(cudaEventSynchronize(S.done[r]));           // results are in the host buffers
+    return 0;
 }
 
 int carenv_observe(void *handle, long long n, const void *poses, const long long *index, float *obs_out,

@@ -19,7 +19,6 @@ Two calling conventions for ``step``:
 from __future__ import annotations
 
 import ctypes as C
-import os
 
 import numpy as np
 import torch
@@ -171,56 +170,33 @@ class VecCarEnv:
         return self._obs, self._rew, term, trunc, self._info_dict(self._info)
 
     def _step_host(self, actions: np.ndarray):
-        """numpy in -> numpy out.  Large batches are cut into env sub-ranges that run on side streams so
-        that the host-side cast and the H2D copy + kernel of range i+1 overlap the D2H copy of range i
-        (the D2H copy of the observations is the bottleneck: 94 B per env over PCIe)."""
+        """numpy in -> numpy out through carenv_step_host: the library narrows the actions into a pinned buffer and
+        pipelines H2D copy, kernel and D2H copies over sub-ranges of the batch (the D2H copy of the observations is
+        the bottleneck: 94 B per env over PCIe); the results land in pinned host tensors owned by this object."""
         n = self.num_envs
         if actions.size != n:
             raise ValueError(f"expected {n} actions, got {actions.size}")
-        dev = self.device
         if self._host is None:
             pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
-            # ~65,536 envs (6 MB of results) per sub-range, at most 8: measured best on B200 / PCIe 5 (1 M envs:
-            # 8 ranges 2.07 ms per step, 4: 2.15, 1: 2.52; 131,072 envs: 2 ranges 0.37 ms, 4: 0.50, 1: 0.40)
-            n_chunks = int(os.environ.get("CARENV_HOST_CHUNKS", 0)) or max(1, min(8, n // 65536))
-            edges = [round(i * n / n_chunks) for i in range(n_chunks + 1)]
-            self._host = dict(act=pin((n,), torch.uint8), obs=pin((n, OBS_DIM), torch.float32),
-                              rew=pin((n,), torch.float32), term=pin((n,), self._term.dtype),
-                              trunc=pin((n,), self._trunc.dtype),
-                              info=pin((n, 4), torch.int32) if self.with_info else None,
-                              dact=torch.empty((n,), dtype=torch.uint8, device=dev),
-                              ranges=list(zip(edges[:-1], edges[1:])),
-                              streams=[torch.cuda.Stream(device=dev) for _ in range(n_chunks)],
-                              ready=torch.cuda.Event(), done=[torch.cuda.Event() for _ in range(n_chunks)])
+            self._host = dict(obs=pin((n, OBS_DIM), torch.float32), rew=pin((n,), torch.float32),
+                              term=pin((n,), self._term.dtype), trunc=pin((n,), self._trunc.dtype),
+                              info=pin((n, 4), torch.int32) if self.with_info else None)
         h = self._host
-        flat = actions.reshape(-1)
-        act_np = h["act"].numpy()
-        flag_code = _lib.FLAG_F32 if self.float_flags else _lib.FLAG_U8
-        cur = torch.cuda.current_stream(dev)
-        h["ready"].record(cur)                     # earlier work on the caller's stream (reset, device steps)
-        for (lo, hi), st, done in zip(h["ranges"], h["streams"], h["done"]):
-            np.copyto(act_np[lo:hi], flat[lo:hi], casting="unsafe")
-            st.wait_event(h["ready"])
-            with torch.cuda.stream(st):
-                h["dact"][lo:hi].copy_(h["act"][lo:hi], non_blocking=True)
-                rc = self._L.carenv_step(self._handle, hi - lo, _ptr(self.pos[lo:hi]), _ptr(self.vel[lo:hi]),
-                                         _ptr(self.ints[lo:hi]), _ptr(h["dact"][lo:hi]), _lib.ACT_U8,
-                                         self.reward_scaling, _ptr(self._obs[lo:hi]), _ptr(self._rew[lo:hi]),
-                                         _ptr(self._term[lo:hi]), _ptr(self._trunc[lo:hi]), flag_code,
-                                         _ptr(self._info[lo:hi]) if self.with_info else None,
-                                         C.c_void_p(st.cuda_stream))
-                _lib.check(rc, "carenv_step")
-                h["obs"][lo:hi].copy_(self._obs[lo:hi], non_blocking=True)
-                h["rew"][lo:hi].copy_(self._rew[lo:hi], non_blocking=True)
-                h["term"][lo:hi].copy_(self._term[lo:hi], non_blocking=True)
-                h["trunc"][lo:hi].copy_(self._trunc[lo:hi], non_blocking=True)
-                if self.with_info:
-                    h["info"][lo:hi].copy_(self._info[lo:hi], non_blocking=True)
-                done.record(st)
-        for done in h["done"]:
-            cur.wait_event(done)                   # later device-side calls see the new state
-        for done in h["done"]:
-            done.synchronize()
+        flat = np.ascontiguousarray(actions.reshape(-1))
+        if flat.dtype == np.uint8:
+            code = _lib.ACT_U8
+        elif flat.dtype == np.int32:
+            code = _lib.ACT_I32
+        else:
+            flat = flat.astype(np.int64, copy=False)
+            code = _lib.ACT_I64
+        with torch.cuda.device(self.device):
+            rc = self._L.carenv_step_host(self._handle, n, _ptr(self.pos), _ptr(self.vel), _ptr(self.ints),
+                                          C.c_void_p(flat.ctypes.data), code, self.reward_scaling, _ptr(h["obs"]),
+                                          _ptr(h["rew"]), _ptr(h["term"]), _ptr(h["trunc"]),
+                                          _lib.FLAG_F32 if self.float_flags else _lib.FLAG_U8,
+                                          _ptr(h["info"]) if self.with_info else None, self._stream())
+        _lib.check(rc, "carenv_step_host")
         flags = (lambda t: t.numpy()) if self.float_flags else (lambda t: t.numpy().view(np.bool_))
         info = self._info_dict(h["info"].numpy()) if self.with_info else {}
         return h["obs"].numpy(), h["rew"].numpy(), flags(h["term"]), flags(h["trunc"]), info

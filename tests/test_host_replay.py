@@ -120,3 +120,24 @@ def test_adversarial_poses_rays_through_vertices_and_at_the_collision_distance(t
     assert np.array_equal(e["obs"][0][~alive], np.broadcast_to(reset_obs, (int((~alive).sum()), 18)))
     assert e["stats"][0] + e["stats"][1] > 200                # the float64 path really was exercised
     assert 0 < alive.sum() < n
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_ring_tracks_match_oracle(tmp_path, seed):
+    """Randomly shaped tracks (segment counts 5..40 per border, wobble, phase): whatever unroll factor and guard
+    bands the host picks for them, the kernel arithmetic follows the float64 oracle."""
+    from tests.synth_tracks import ring_track
+
+    rng = np.random.default_rng(1000 + seed)
+    n_outer, n_inner = int(rng.integers(5, 41)), int(rng.integers(5, 41))
+    path = ring_track(str(tmp_path / "ring.json"), n_outer, n_inner, n_gates=int(rng.integers(4, 30)),
+                      wobble=float(rng.uniform(0.0, 0.12)), seed_phase=float(rng.uniform(0.0, 1.5)))
+    p = rng.dirichlet(np.ones(9) * 2.0)
+    acts = rng.choice(9, size=(500, 384), p=p).astype(np.uint8)
+    ora = COracleVecEnv(384, path, scan_all_gates=True)
+    ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    e = emul_rollout(path, acts)
+    got = dict(obs=e["obs"], rew=e["rew"], term=e["term"], trunc=e["trunc"], gates_passed=e["info"][..., 0],
+               time_passed=e["info"][..., 1], next_gate_index=e["info"][..., 2])
+    assert_trajectory_matches(got, ref, what=f"ring {n_outer}+{n_inner} (seed {seed})")

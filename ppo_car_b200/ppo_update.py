@@ -50,6 +50,13 @@ class FusedPPOUpdate:
 
     def grad(self, obs, idx, act, old_logp, adv, ret, obs_is_gathered: bool = False):
         """Gradients of one minibatch into ``self.grads``.  ``idx`` [batch] int64 indexes the flat arrays."""
+        if idx.dtype != torch.int64 or idx.numel() != self.batch or not idx.is_contiguous() or idx.device != self.device:
+            raise ValueError(f"idx must be a contiguous int64 tensor of {self.batch} elements on {self.device}")
+        for name, t in (("obs", obs), ("act", act), ("old_logp", old_logp), ("adv", adv), ("ret", ret)):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"{name} must be a contiguous float32 tensor on {self.device}")
+        if obs.shape[-1] != 18 or (obs_is_gathered and obs.numel() != self.batch * 18):
+            raise ValueError("obs must have 18 columns (and `batch` rows when it is already gathered)")
         with torch.cuda.device(self.device):
             rc = self.L.carenv_ppo_grad(*[_p(p) for p in self.params], _p(obs), int(obs_is_gathered), _p(idx), _p(act),
                                         _p(old_logp), _p(adv), _p(ret), self.batch, self.clip_ratio, self.vf_coef,

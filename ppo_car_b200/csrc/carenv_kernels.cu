@@ -6,8 +6,16 @@
 //               segment coordinate is a uniform operand of the FMA-pipe instructions; the
 //               per-thread-indexed tables (72 headings, gates) are staged once per block into
 //               shared memory.
+//   k_rollout_warp   small batches (<= 2,048 envs, <= 32 wall segments): one WARP per environment, lane = wall
+//               segment, per-ray extrema by integer REDUX; bit-identical to k_rollout.
+//   k_observe   observations recomputed from 32-byte pose records (compact rollout storage).
 //   k_reset     CarEnv.reset for every environment.
 //   k_gae       Buffer.calculate_advantages as a reverse scan, one thread per environment column.
+//   k_policy_rollout / k_policy_rollout_tc   policy forward + sampling + env step + Buffer rows in one launch
+//               (CUDA cores / tcgen05 tensor cores, csrc/policy_core.cuh, csrc/tc_mlp.cuh); k_pack_policy packs the
+//               network parameters for them.
+//   k_ppo_*     fused PPO minibatch update (csrc/ppo_update.cuh).
+//   carenv_step_host   the host-buffer step: sub-range pipeline of narrowing, H2D, kernel and D2H copies.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --shared -Xcompiler -fPIC
 #include <cuda_runtime.h>

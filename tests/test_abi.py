@@ -32,6 +32,25 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert _lib.lib().carenv_abi_version() == 1
 
 
+def test_ctypes_bindings_have_the_declared_argument_counts():
+    """Every prototype of include/carenv_b200.h that ppo_car_b200/_lib.py binds with argtypes has as many
+    parameters in the header as in the binding (guards against the two drifting apart)."""
+    text = open(os.path.join(ROOT, "include", "carenv_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(?:int|const char \*)\s*\*?\s*(carenv_\w+|gae_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S))
+    L = _lib.lib()
+    checked = 0
+    for name, params in protos.items():
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue
+        params = params.strip()
+        n_decl = 0 if params in ("", "void") else params.count(",") + 1
+        assert len(fn.argtypes) == n_decl, (name, len(fn.argtypes), n_decl)
+        checked += 1
+    assert checked >= 15
+
+
 def test_library_contains_sm100a_code():
     out = os.popen(f"cuobjdump -lelf {ppo_car_b200.build()} 2>/dev/null").read()
     assert "sm_100a" in out

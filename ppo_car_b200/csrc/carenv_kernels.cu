@@ -793,8 +793,8 @@ k_gae(const float *__restrict__ rew, const float *__restrict__ val, const float 
       const float *__restrict__ trunc, const float *__restrict__ last_val, const float *__restrict__ last_term,
       const float *__restrict__ last_trunc, float *__restrict__ adv, float *__restrict__ ret, int T, int N, float g,
       float gl) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= N) return;
+  // grid-stride over the columns: the launch sizes the grid to ONE balanced wave of resident threads
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < N; e += gridDim.x * blockDim.x) {
     float nv = last_val[e];
     float tm = __fadd_rn(1.0f, -last_term[e]);
     float um = __fadd_rn(1.0f, -last_trunc[e]);
@@ -829,6 +829,7 @@ k_gae(const float *__restrict__ rew, const float *__restrict__ val, const float 
         tm = __fadd_rn(1.0f, -__ldcs(term + k));
         um = __fadd_rn(1.0f, -__ldcs(trunc + k));
     }
+  }
 }
 
 // FP32-pipe peak probe: kFfmaChains independent FFMA chains per thread, no memory traffic.
@@ -1371,11 +1372,25 @@ int gae_reverse_scan(const float *rew, const float *val, const float *term, cons
         return fail(CARENV_E_INVAL, "null pointer");
     const float g = (float)gamma;
     const float gl = (float)(gamma * gae_lambda);   // evaluated in double first (lib/buffer.py:61)
-    // 64-thread blocks: 1,024 blocks at N = 65,536 balance over 148 SMs (6.9 per SM) better than 512 blocks of 128
-    // (3.5 per SM): 6.05 vs 5.93 TB/s measured at [1024, 65536]
+    // 64-thread blocks (1,024 blocks at N = 65,536 balance over 148 SMs better than 512 blocks of 128: 6.05 vs 5.93
+    // TB/s) and one wave: when there are more columns than resident threads every thread takes k columns, so that
+    // no SM idles through a partial last wave (N = 131,072: 2 columns per thread)
     const int block = 64;
-    const int grid = (N + block - 1) / block;
-    const bool wide = N >= 100000;
+    // long scans (T >= 512): unroll 8 and one wave; short, very wide ones ([128, 1 M]): one column per thread and the
+    // 16-deep variant, whose per-column fill / drain is amortised by the many waves (6.07 vs 5.23 TB/s)
+    const bool one_wave = T >= 512;
+    const bool wide = !one_wave && N >= 100000;
+    int threads = N;
+    if (one_wave) {
+        int dev = 0, sms = 148, per_sm = 8;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gae<8>, block, 0);
+        const long long cap = (long long)(per_sm > 0 ? per_sm : 1) * sms * block;
+        const int k = (int)((N + cap - 1) / cap);
+        threads = (N + k - 1) / k;
+    }
+    const int grid = (threads + block - 1) / block;
     if (wide)
         k_gae<16><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(rew, val, term, trunc, last_val, last_term,
                                                                        last_trunc, adv, ret, T, N, g, gl);

@@ -1,9 +1,14 @@
-"""TEST INFRASTRUCTURE (container-only): import the UNMODIFIED reference CarEnv.
+"""TEST INFRASTRUCTURE: import the UNMODIFIED reference CarEnv / Buffer.
 
-This module is used only by ``tests/golden/make_golden.py`` and by the optional
-``-m "not gpu"`` cross-checks that run when ``/root/reference`` is mounted.  It is
-never imported by the product package and never runs on the GPU box (the reference
-tree does not exist there).
+Two places can hold the reference files:
+
+  * ``/root/reference`` (or ``$PPO_CAR_REFERENCE``) — the read-only mount of the build container;
+  * ``oracle/_ref/`` — a byte-for-byte copy of the four hot-path files made by ``oracle/make_ref.py``
+    (git-ignored, travels to the GPU box with the snapshot), verified against its MANIFEST.json.
+
+Used by ``tests/`` (golden-vector generation, live cross-checks of the port AND of the CUDA path),
+and by ``bench.py``'s CPU legs (``cpu_baseline``, ``--impl reference``: the reference's own classes
+timed on the host cores).  It is never imported by the product package ``ppo_car_b200``.
 
 The reference's ``lib/car_env.py`` imports ``gymnasium`` and ``pygame``
 (lib/car_env.py:4-7), neither of which is installed.  Only a base class, two
@@ -15,15 +20,50 @@ own code running on numpy.
 """
 from __future__ import annotations
 
+import hashlib
+import json
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PPO_CAR_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_MOUNT = os.environ.get("PPO_CAR_REFERENCE", "/root/reference")
+_COPY = os.path.join(_HERE, "_ref")
+
+
+def _copy_is_intact() -> bool:
+    try:
+        man = json.load(open(os.path.join(_COPY, "MANIFEST.json")))
+        for rel, digest in man["files"].items():
+            with open(os.path.join(_COPY, rel), "rb") as fh:
+                if hashlib.sha256(fh.read()).hexdigest() != digest:
+                    return False
+        return "lib/car_env.py" in man["files"]
+    except Exception:
+        return False
+
+
+def reference_root(prefer_copy: bool = False) -> str | None:
+    """Directory holding lib/car_env.py: the mount when present, else the verified oracle/_ref copy."""
+    mount_ok = os.path.isfile(os.path.join(_MOUNT, "lib", "car_env.py"))
+    if mount_ok and not prefer_copy:
+        return _MOUNT
+    if _copy_is_intact():
+        return _COPY
+    return _MOUNT if mount_ok else None
+
+
+REFERENCE_ROOT = reference_root() or _MOUNT
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "lib", "car_env.py"))
+    return reference_root() is not None
+
+
+def reference_kind() -> str:
+    """"mount" (/root/reference), "copy" (oracle/_ref) or "absent"."""
+    root = reference_root()
+    return "absent" if root is None else ("mount" if root == _MOUNT else "copy")
 
 
 def _install_stubs() -> None:
@@ -75,11 +115,12 @@ def _install_stubs() -> None:
 
 def import_reference():
     """Return (CarEnv class, Buffer class) from the unmodified reference tree."""
-    if not reference_available():
-        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError(f"reference not found: neither {_MOUNT} nor an intact {_COPY} (python oracle/make_ref.py)")
     _install_stubs()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     from lib.car_env import CarEnv  # type: ignore
     from lib.buffer import Buffer  # type: ignore
 
@@ -87,7 +128,7 @@ def import_reference():
 
 
 def track_path(name: str) -> str:
-    return os.path.join(REFERENCE_ROOT, "tracks", name)
+    return os.path.join(reference_root() or _MOUNT, "tracks", name)
 
 
 class RefVecEnv:

@@ -22,7 +22,7 @@ ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
 FLAG_U8, FLAG_F32 = 0, 1
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--shared",
-              "-Xcompiler", "-fPIC", "-std=c++17"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-std=c++17"]
 
 _lib = None
 

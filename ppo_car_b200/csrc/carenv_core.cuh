@@ -47,6 +47,13 @@ constexpr int kHeadings = 72;      // 360 / 5 degrees
 constexpr int kMaxSeg = 128;       // wall segments carried in kernel-parameter space (fast kernels)
 constexpr int kMaxBigSeg = 2048;   // larger tracks: geometry staged in shared memory, generic loop (U = 0)
 constexpr int kTimeLimit = 1000;   // lib/car_env.py:491
+// The signed line offsets q are carried scaled by 2^50 (an exact scaling): the hit test "q(A) and q(B) have
+// opposite signs" then is ONE saturating multiply, mask = sat(q'(A) * -q'(B)) in {0, 1}  (|q'(A) q'(B)| >= 1
+// unless some |q| < 2^-50, far inside the eps_q guard band), instead of a multiply and a compare.  The
+// denominators cross(e, d) and the ray-independent numerators cross(e, A - pos) are scaled alike, so that
+// r = den' / un' is unchanged bit for bit.
+constexpr float kQScale = 1125899906842624.0f;      // 2^50
+constexpr double kQScaleD = 1125899906842624.0;
 
 struct F2 { float x, y; };
 struct D2 { double x, y; };
@@ -68,7 +75,7 @@ CE_HD SegHead seg_head(const SegF &f) {
 #else
 CE_HD SegHead seg_head(const SegF &f) { return SegHead{f.bhx, f.bhy, f.ney, f.ey}; }
 #endif
-struct SegD { double K, ex, ey; };   // K = cross(e, A):  cross(e, A - pos) = K - (ex*py - ey*px)   // K = cross(e, A):  cross(e, A - pos) = K - (ex*py - ey*px)
+struct SegD { double K, ex, ey; };   // 2^50 * (cross(e, A), ex, ey):  un' = 2^50 * cross(e, A - pos) = K - (ex*py - ey*px)
 
 struct GateRec { double x1, y1, x2, y2; float ex, ey, len, pad; };
 
@@ -78,14 +85,15 @@ struct TrackParams {
     float coll_band;    // relative half-width of the band around d == 10
     float tiny_d;       // distances below this are re-evaluated (sign of u uncertain)
     float gate_band;    // gate margin band, in units of the gate length
-    float tiny_un;      // |cross(e, A')| below this: every line is re-evaluated
+    float tiny_un;      // |2^50 cross(e, A')| below this: every line is re-evaluated
     int unroll;         // first U of {6, 4, 2, 1} such that n_seg and every polyline start are multiples of U;
                         // 0 for tracks with more than kMaxSeg segments (geometry from Tables::segf/segd)
     int unroll4;        // same, restricted to {4, 2, 1} (the fused rollout kernels)
     int pad2;
     double start_x, start_y;
     float reset_obs[kObsDim];
-    float pad1[2];
+    float eps_qs;       // 2^50 * eps_q: the guard on the scaled offsets q' of the wall tests
+    float pad1;
     SegF segf[kMaxSeg];
     SegD segd[kMaxSeg];
 };
@@ -94,6 +102,7 @@ struct TrackParams {
 // host side of the handle, staged to shared memory by the kernels.
 struct Tables {
     const F2 *trig32;        // [72] (cos, sin) of radians(initial_angle + 5k), float32
+    const F2 *trig32s;       // [72] the same scaled by 2^50 (directions of the wall tests, see kQScale)
     const D2 *trig64;        // [72] same, float64
     const D2 *acc64;         // [72] (cos*0.8, sin*0.8), float64  (lib/car_env.py:430)
     const GateRec *gates;    // [n_gates]
@@ -176,7 +185,12 @@ CE_HD P2 padd(P2 a, P2 b) { return p2(a.x + b.x, a.y + b.y); }
 CE_HD float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 CE_HD float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 #endif
-CE_HD float neg_mask(float w) { return w < 0.0f ? 1.0f : 0.0f; }   // FSET.BF.LT
+// mask = clamp(a * b, 0, 1): FMUL.SAT, one FMA-pipe instruction (a NaN product cannot occur: q is finite)
+#if defined(__CUDA_ARCH__)
+CE_HD float sat_mul(float a, float b) { float r; asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+#else
+CE_HD float sat_mul(float a, float b) { const float p = a * b; return p > 1.0f ? 1.0f : (p > 0.0f ? p : 0.0f); }
+#endif
 
 CE_HD int wrap72(int k) { return k >= kHeadings ? k - kHeadings : (k < 0 ? k + kHeadings : k); }
 
@@ -275,15 +289,15 @@ CE_HD void integrate(EnvState &s, int thrust, int k_pre, const Tables &T) {
 
 // ---- the 12 ray distances and the wall-collision decision -------------------------------------
 struct WallAcc {
-    float c[3], sn[3];      // directions of lines 0..2 (heading + 0/30/60 deg); lines 3..5 are these rotated by 90 deg
+    float c[3], sn[3];      // 2^50 * directions of lines 0..2 (heading + 0/30/60 deg); lines 3..5 are these rotated by 90 deg
     float phx, phy;         // float32(pos)
     float Rp[6], Rm[6];     // max of r = 1/u over hits with u > 0 (ray l) / min over hits with u < 0 (ray l+6)
-    float gq[6];            // min |q| per line  -> hit/miss guard
-    float gu;               // min |cross(e, A')| -> sign-of-u guard
-    float qa[6];            // q of the previous endpoint on each line
+    float gq[6];            // min |q'| per line  -> hit/miss guard
+    float gu;               // min |un'| -> sign-of-u guard
+    float qa[6];            // q' of the previous endpoint on each line
 };
 
-// q of one endpoint on the six lines.  Only the SIGN of q is used (and |q| for the guard), so the
+// q' = 2^50 q of one endpoint on the six lines.  Only the SIGN of q is used (and |q| for the guard), so the
 // endpoint is localised with a single float32 subtraction: |dq| <= 6.1e-4 px for |P - pos| <= 1500 px
 // (rounding of P, of pos, of the difference, of the two products and of the direction), below eps_q.
 CE_HD void wall_point(const WallAcc &w, float hx, float hy, float q[6]) {
@@ -302,6 +316,14 @@ CE_HD void wall_chain_start(WallAcc &w, const SegF &f) {
     for (int l = 0; l < 6; ++l) w.gq[l] = fminf(w.gq[l], fabsf(w.qa[l]));
 }
 
+// The float32 denominators 2^50 cross(e, d) of one segment for one heading: (line l, line l + 3).  This is THE
+// definition — the kernels that take them from the per-track table (TabView) read values computed by this very
+// function on the host, so table and arithmetic paths agree bit for bit.
+CE_HD void seg_den(float ex, float ey, float sn, float c, float &den0, float &den3) {
+    den0 = ffma(ex, sn, -fmul(ey, c));
+    den3 = ffma(ex, c, fmul(ey, sn));
+}
+
 // One wall segment against the six lines.
 // GUARD: 1 = fold |q| of this segment's end point into the guard, 2 = fold |q| of BOTH end points
 // (one 3-input min per line covers two polyline points), 0 = leave it to the next segment's GUARD 2.
@@ -309,7 +331,7 @@ template <int GUARD>
 CE_HD void wall_segment(WallAcc &w, const SegF &f, const SegD &g, double px, double py) {
     float qb[6];
     wall_point(w, f.bhx, f.bhy, qb);
-    // cross(e, A - pos) in float64 (two FMAs on the FP64 pipe), rounded once, one float32 reciprocal
+    // 2^50 cross(e, A - pos) in float64 (two FMAs on the FP64 pipe), rounded once, one float32 reciprocal
     const float un = (float)dfma(g.ey, px, dfma(-g.ex, py, g.K));
     const float inv = frcp(un);
     w.gu = fminf(w.gu, fabsf(un));
@@ -317,10 +339,12 @@ CE_HD void wall_segment(WallAcc &w, const SegF &f, const SegD &g, double px, dou
     for (int l = 0; l < 3; ++l) {
         // cross(e, d_l) / cross(e, A') = 1/u.  (Pre-scaling e by inv would save a multiply per test but
         // measurably costs accuracy: 1.2e-5 instead of 1.6e-6 worst relative distance error.)
-        const float r0 = fmul(ffma(f.ex, w.sn[l], -fmul(f.ey, w.c[l])), inv);
-        const float r3 = fmul(ffma(f.ex, w.c[l], fmul(f.ey, w.sn[l])), inv);
-        if (fmul(w.qa[l], qb[l]) < 0.0f) { w.Rp[l] = fmaxf(w.Rp[l], r0); w.Rm[l] = fminf(w.Rm[l], r0); }
-        if (fmul(w.qa[l + 3], qb[l + 3]) < 0.0f) { w.Rp[l + 3] = fmaxf(w.Rp[l + 3], r3); w.Rm[l + 3] = fminf(w.Rm[l + 3], r3); }
+        float den0, den3;
+        seg_den(f.ex, f.ey, w.sn[l], w.c[l], den0, den3);
+        const float h0 = fmul(fmul(den0, inv), sat_mul(w.qa[l], -qb[l]));            // r * (hit ? 1 : 0)
+        const float h3 = fmul(fmul(den3, inv), sat_mul(w.qa[l + 3], -qb[l + 3]));
+        w.Rp[l] = fmaxf(w.Rp[l], h0); w.Rm[l] = fminf(w.Rm[l], h0);
+        w.Rp[l + 3] = fmaxf(w.Rp[l + 3], h3); w.Rm[l + 3] = fminf(w.Rm[l + 3], h3);
     }
 #pragma unroll
     for (int l = 0; l < 6; ++l) {
@@ -332,14 +356,27 @@ CE_HD void wall_segment(WallAcc &w, const SegF &f, const SegD &g, double px, dou
 
 // Two consecutive segments j, j+1 of one polyline, packed: the lines l and l+3 (perpendicular) share
 // one FFMA2/FMUL2 each because q_l = x*s_l - y*c_l and q_{l+3} = x*c_l + y*s_l are the two components of
-// x*(s_l, c_l) + y*(-c_l, s_l).  Hits are selected arithmetically (r * mask, mask in {0,1} from FSET) so
+// x*(s_l, c_l) + y*(-c_l, s_l).  Hits are selected arithmetically (r * mask, mask in {0,1} from FMUL.SAT) so
 // that one 3-input max/min per ray folds both segments.  Every component is the same IEEE operation as
 // in wall_segment, so both paths give bit-identical results.
 struct WallAcc2 {
-    P2 S[3];                // S_l = (s_l, c_l); its half-swap (c_l, s_l) is a free operand modifier
+    P2 S[3];                // S_l = 2^50 (s_l, c_l); its half-swap (c_l, s_l) is a free operand modifier
     float phx, phy;         // float32(pos)
     float Rp[6], Rm[6], gq[6], gu;
-    P2 QA[3];               // (q_l, q_{l+3}) of the previous endpoint
+    P2 QA[3];               // (q'_l, q'_{l+3}) of the previous endpoint
+};
+
+// Per-track table of the denominators for the thread-per-environment kernel (k_rollout_tab): row k (heading
+// index), entry jp (segment pair) = (den_l(2jp), den_{l+3}(2jp), den_l(2jp+1), den_{l+3}(2jp+1)) as seg_den computes
+// them.  The kernel keeps `copies` skewed copies in shared memory (copy c starts one 16-byte bank group after
+// copy c - 1, rows are multiples of 128 bytes) and thread t reads copy t % 8: the eight threads of a quarter warp
+// then hit eight different bank groups whatever their headings are — a conflict-free LDS.128 per pair and line.
+#if !defined(__CUDACC__)
+struct float4 { float x, y, z, w; };
+#endif
+struct TabView {
+    const float4 *base;     // this thread's copy
+    int row_f4;             // float4 per row
 };
 
 // (q_l, q_{l+3}) = x*(s_l, c_l) + (-y, y)*(c_l, s_l): only S_l is kept in registers (keeping the rotated
@@ -359,8 +396,11 @@ CE_HD void wall_chain_start2(WallAcc2 &w, const SegF &f) {
     }
 }
 
+// TAB: the denominators come from the table rows tb[l] (entry jp) instead of one FMUL2 + FFMA2 per segment and
+// line pair — same values (seg_den), 4 packed FMA-pipe instructions less per pair and line.
+template <bool TAB>
 CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1, const SegD &g1, double px,
-                     double py) {
+                     double py, const float4 *const *tb = nullptr, int jp = 0) {
     P2 QB0[3], QB1[3];
     const SegHead h0 = seg_head(f0), h1 = seg_head(f1);     // bhx, bhy, -ey, ey: one 128-bit uniform load each
     wall_point2(w, h0.bhx, h0.bhy, QB0);
@@ -371,12 +411,18 @@ CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1
     w.gu = fmin3(w.gu, fabsf(un0), fabsf(un1));
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
-        const P2 SW = p2(w.S[l].y, w.S[l].x);
-        const P2 R0 = pmul(pfma(p2(f0.ex, f0.ex), w.S[l], pmul(p2(h0.ney, h0.ey), SW)), p2(inv0, inv0));
-        const P2 R1 = pmul(pfma(p2(f1.ex, f1.ex), w.S[l], pmul(p2(h1.ney, h1.ey), SW)), p2(inv1, inv1));
-        const P2 W0 = pmul(w.QA[l], QB0[l]), W1 = pmul(QB0[l], QB1[l]);
-        const P2 H0 = pmul(R0, p2(neg_mask(W0.x), neg_mask(W0.y)));
-        const P2 H1 = pmul(R1, p2(neg_mask(W1.x), neg_mask(W1.y)));
+        P2 D0, D1;
+        if (TAB) {
+            const float4 t = tb[l][jp];
+            D0 = p2(t.x, t.y); D1 = p2(t.z, t.w);
+        } else {
+            const P2 SW = p2(w.S[l].y, w.S[l].x);
+            D0 = pfma(p2(f0.ex, f0.ex), w.S[l], pmul(p2(h0.ney, h0.ey), SW));
+            D1 = pfma(p2(f1.ex, f1.ex), w.S[l], pmul(p2(h1.ney, h1.ey), SW));
+        }
+        const P2 R0 = pmul(D0, p2(inv0, inv0)), R1 = pmul(D1, p2(inv1, inv1));
+        const P2 H0 = pmul(R0, p2(sat_mul(w.QA[l].x, -QB0[l].x), sat_mul(w.QA[l].y, -QB0[l].y)));
+        const P2 H1 = pmul(R1, p2(sat_mul(QB0[l].x, -QB1[l].x), sat_mul(QB0[l].y, -QB1[l].y)));
         w.Rp[l] = fmax3(w.Rp[l], H0.x, H1.x); w.Rm[l] = fmin3(w.Rm[l], H0.x, H1.x);
         w.Rp[l + 3] = fmax3(w.Rp[l + 3], H0.y, H1.y); w.Rm[l + 3] = fmin3(w.Rm[l + 3], H0.y, H1.y);
         w.gq[l] = fmin3(w.gq[l], fabsf(QB0[l].x), fabsf(QB1[l].x));
@@ -407,7 +453,7 @@ __device__ __forceinline__ void cast_walls_warp(const EnvState &s, const Tables 
     w.phx = (float)s.px; w.phy = (float)s.py;
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
-        const F2 d = T.trig32[wrap72(s.k + 6 * l)];
+        const F2 d = T.trig32s[wrap72(s.k + 6 * l)];
         w.c[l] = d.x; w.sn[l] = d.y;
     }
     float qa[6], qb[6];
@@ -419,11 +465,12 @@ __device__ __forceinline__ void cast_walls_warp(const EnvState &s, const Tables 
     float rp[6], rm[6], g[6];
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
-        const float r0 = fmul(ffma(ws.f.ex, w.sn[l], -fmul(ws.f.ey, w.c[l])), inv);
-        const float r3 = fmul(ffma(ws.f.ex, w.c[l], fmul(ws.f.ey, w.sn[l])), inv);
-        const bool h0 = on && fmul(qa[l], qb[l]) < 0.0f, h3 = on && fmul(qa[l + 3], qb[l + 3]) < 0.0f;
-        rp[l] = h0 ? fmaxf(R0, r0) : R0;          rm[l] = h0 ? fminf(-R0, r0) : -R0;
-        rp[l + 3] = h3 ? fmaxf(R0, r3) : R0;      rm[l + 3] = h3 ? fminf(-R0, r3) : -R0;
+        float den0, den3;
+        seg_den(ws.f.ex, ws.f.ey, w.sn[l], w.c[l], den0, den3);
+        const float h0 = on ? fmul(fmul(den0, inv), sat_mul(qa[l], -qb[l])) : 0.0f;
+        const float h3 = on ? fmul(fmul(den3, inv), sat_mul(qa[l + 3], -qb[l + 3])) : 0.0f;
+        rp[l] = fmaxf(R0, h0);          rm[l] = fminf(-R0, h0);
+        rp[l + 3] = fmaxf(R0, h3);      rm[l + 3] = fminf(-R0, h3);
     }
 #pragma unroll
     for (int l = 0; l < 6; ++l) g[l] = on ? fminf(fabsf(qa[l]), fabsf(qb[l])) : 1.0e30f;
@@ -442,9 +489,10 @@ __device__ __forceinline__ void cast_walls_warp(const EnvState &s, const Tables 
 // n_seg and every polyline start are multiples of U; the body is then U segments of straight-line
 // code (about 1.5 KB each) — small enough to stay in the instruction cache, which a full unroll of
 // 24 segments is not (measured: 1.5 "no instruction" stalls per issue and a slower kernel).
-template <int U>
+// TAB (U > 1 only): denominators from the per-track table `tv` (k_rollout_tab) instead of being recomputed.
+template <int U, bool TAB = false>
 CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, float dist[kNumRays],
-                      unsigned long long *stats, const WarpSeg *ws = nullptr) {
+                      unsigned long long *stats, const WarpSeg *ws = nullptr, const TabView *tv = nullptr) {
     const float R0 = 1.0e-3f;           // 1/1000: "no hit" (lib/car_env.py:198)
     float Rp[6], Rm[6], gq[6], gu;
     if (U == kWarpPerEnv) {
@@ -458,11 +506,14 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
     } else if (U > 1) {
         WallAcc2 w;
         w.phx = (float)s.px; w.phy = (float)s.py;
+        const float4 *tb[3] = {nullptr, nullptr, nullptr};
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
-            const F2 d = T.trig32[wrap72(s.k + 6 * l)];
+            const int kl = wrap72(s.k + 6 * l);
+            const F2 d = T.trig32s[kl];
             w.S[l] = p2(d.y, d.x);
             w.QA[l] = p2(0.0f, 0.0f);
+            if (TAB) tb[l] = tv->base + kl * tv->row_f4;
         }
 #pragma unroll
         for (int l = 0; l < 6; ++l) { w.Rp[l] = R0; w.Rm[l] = -R0; w.gq[l] = 1.0e30f; }
@@ -472,7 +523,8 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
             if (P.segf[j0].chain_start) wall_chain_start2(w, P.segf[j0]);
 #pragma unroll
             for (int u = 0; u < U; u += 2)
-                wall_pair(w, P.segf[j0 + u], P.segd[j0 + u], P.segf[j0 + u + 1], P.segd[j0 + u + 1], s.px, s.py);
+                wall_pair<TAB>(w, P.segf[j0 + u], P.segd[j0 + u], P.segf[j0 + u + 1], P.segd[j0 + u + 1], s.px, s.py,
+                               tb, (j0 + u) >> 1);
         }
 #pragma unroll
         for (int l = 0; l < 6; ++l) { Rp[l] = w.Rp[l]; Rm[l] = w.Rm[l]; gq[l] = w.gq[l]; }
@@ -482,7 +534,7 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
         w.phx = (float)s.px; w.phy = (float)s.py;
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
-            const F2 d = T.trig32[wrap72(s.k + 6 * l)];
+            const F2 d = T.trig32s[wrap72(s.k + 6 * l)];
             w.c[l] = d.x; w.sn[l] = d.y;
         }
 #pragma unroll
@@ -526,14 +578,14 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
         dist[l] = Rp[l] > R0 ? frcp(Rp[l]) : 1000.0f;
         dist[l + 6] = Rm[l] < -R0 ? -frcp(Rm[l]) : 1000.0f;
     }
-    const bool careful = (gu < P.tiny_un) || (g_all < P.eps_q) || (r_all > r_tiny) || (band_lo < r_band);
+    const bool careful = (gu < P.tiny_un) || (g_all < P.eps_qs) || (r_all > r_tiny) || (band_lo < r_band);
     if (careful) {
         const bool redo_all = gu < P.tiny_un;     // car (numerically) on a wall line: sign of u unknown
         destroyed = false;
 #pragma unroll
         for (int l = 0; l < 6; ++l) {
             const bool cardinal = (l == 0 || l == 3);
-            bool redo = redo_all || (gq[l] < P.eps_q);
+            bool redo = redo_all || (gq[l] < P.eps_qs);
             if (redo) stat_add(stats, kStatLine);
             if (!redo && (Rp[l] > r_tiny || Rm[l] < -r_tiny)) { redo = true; stat_add(stats, kStatTiny); }
             if (!redo && cardinal &&
@@ -568,9 +620,9 @@ CE_HD void pose_observation(const EnvState &s, float vx10, float vy10, const flo
 }
 
 // ---- one CarEnv.step with same-step autoreset --------------------------------------------------
-template <int U>
+template <int U, bool TAB = false>
 CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackParams &P, const Tables &T,
-                    StepResult &o, unsigned long long *stats, const WarpSeg *ws = nullptr) {
+                    StepResult &o, unsigned long long *stats, const WarpSeg *ws = nullptr, const TabView *tv = nullptr) {
     int thrust, turn;
     decode_action(action, thrust, turn);
     double reward = thrust > 0 ? 0.01 : 0.0;
@@ -589,7 +641,7 @@ CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackPar
     integrate(s, thrust, k_pre, T);
 
     float dist[kNumRays];
-    bool destroyed = cast_walls<U>(s, P, T, dist, stats, ws);
+    bool destroyed = cast_walls<U, TAB>(s, P, T, dist, stats, ws, tv);
     destroyed = destroyed || (P.start_destroyed != 0);
     s.t += 1;
     o.terminated = 0; o.truncated = 0;

@@ -57,7 +57,9 @@ int cuda_fail(cudaError_t e, const char *what) {
 struct Handle {
     int device;
     HostTrack host;
-    unsigned char *d_blob;    // trig64 | acc64 | gates | trig32 | walls64 | segf | segd
+    unsigned char *d_blob;    // trig64 | acc64 | gates | trig32 | trig32s | walls64 | segf | segd | den4
+    const float4 *d_den4;     // [72][n_pairs] denominators of the pair kernels (null: track without pairs)
+    int tab;                  // 0 = k_rollout_tab for large launches, 1 = always (where the track allows), -1 = never
     Tables dev;               // device pointers into d_blob
     unsigned long long *d_stats;
     size_t smem_bytes;
@@ -149,7 +151,8 @@ __device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, int
     D2 *s_acc64 = s_trig64 + kHeadings;
     GateRec *s_gates = reinterpret_cast<GateRec *>(s_acc64 + kHeadings);
     F2 *s_trig32 = reinterpret_cast<F2 *>(s_gates + n_gates);
-    double *s_walls = reinterpret_cast<double *>(s_trig32 + kHeadings);   // float64 walls for the exact path: a
+    F2 *s_trig32s = s_trig32 + kHeadings;
+    double *s_walls = reinterpret_cast<double *>(s_trig32s + kHeadings);   // float64 walls for the exact path: a
     const int n64a = kHeadings * 2, n64g = n_gates * (int)(sizeof(GateRec) / 8);   // global-memory copy costs ~10 k cycles per fallback
     double *d0 = reinterpret_cast<double *>(s_trig64);
     double *d1 = reinterpret_cast<double *>(s_acc64);
@@ -161,7 +164,7 @@ __device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, int
     const double *g3 = reinterpret_cast<const double *>(G.trig32);
     for (int i = threadIdx.x; i < n64a; i += blockDim.x) { d0[i] = g0[i]; d1[i] = g1[i]; }
     for (int i = threadIdx.x; i < n64g; i += blockDim.x) d2[i] = g2[i];
-    for (int i = threadIdx.x; i < kHeadings; i += blockDim.x) d3[i] = g3[i];
+    for (int i = threadIdx.x; i < 2 * kHeadings; i += blockDim.x) d3[i] = g3[i];   // trig32 | trig32s (contiguous in the blob)
     for (int i = threadIdx.x; i < 4 * n_seg; i += blockDim.x) s_walls[i] = G.walls64[i];
     const SegF *s_segf = nullptr;
     const SegD *s_segd = nullptr;
@@ -175,7 +178,7 @@ __device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, int
         s_segd = reinterpret_cast<const SegD *>(d5);
     }
     __syncthreads();
-    return Tables{s_trig32, s_trig64, s_acc64, s_gates, s_walls, s_segf, s_segd};
+    return Tables{s_trig32, s_trig32s, s_trig64, s_acc64, s_gates, s_walls, s_segf, s_segd};
 }
 
 // What k_rollout writes per env-step besides reward and flags (rollout storage format).
@@ -263,6 +266,71 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
     pos[e] = make_double2(s.px, s.py);
     vel[e] = make_double2(s.vx, s.vy);
     ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+}
+
+// Large launches on tracks the pair kernels take (<= 128 segments, even chain lengths): thread per environment
+// like k_rollout, but the 144 denominators cross(e, d) a step needs come from a per-track table in shared memory
+// (TabView, carenv_core.cuh) instead of 144 FMUL2 / FFMA2 — the values are the same bit for bit.  One CTA of up to
+// 512 threads per SM owns the table copies (72 headings x n_pairs x 16 B, x 8 skewed copies = 147 KB on big_track)
+// and walks over blocks of `envs_per_block` environments; the block size is chosen on the host so that every SM
+// gets the same number of blocks (no partial last wave: 131,072 envs are 2 x 148 blocks of 443).
+constexpr int kTabThreads = 512;
+template <typename ActT, typename FlagT, int U>
+__global__ void __launch_bounds__(kTabThreads, 1)
+k_rollout_tab(const __grid_constant__ TrackParams P, const Tables G, const float4 *__restrict__ den4, int n_pairs,
+              int row_f4, int copies, int table_bytes, int n_envs, int n_steps, int envs_per_block, int n_blocks,
+              double2 *__restrict__ pos, double2 *__restrict__ vel, int4 *__restrict__ ints,
+              const ActT *__restrict__ actions, double reward_scale, float *__restrict__ obs_out,
+              float *__restrict__ rew_out, FlagT *__restrict__ term_out, FlagT *__restrict__ trunc_out,
+              int4 *__restrict__ info_out, unsigned long long *stats, int obs_mode) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    // [tables | pad to 128 B | copy 0 | copy 1 (+16 B) | ...]: copy c starts at c * (72 * row + 1) float4
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
+    const int t_off = (int)(((s0 + (uint32_t)table_bytes + 127u) & ~127u) - s0);
+    float4 *tab = reinterpret_cast<float4 *>(smem + t_off);
+    const int copy_f4 = kHeadings * row_f4 + 1;
+    for (int i = threadIdx.x; i < kHeadings * n_pairs; i += blockDim.x) {
+        const float4 v = den4[i];
+        const int k = i / n_pairs, jp = i - k * n_pairs;
+        for (int c = 0; c < copies; ++c) tab[c * copy_f4 + k * row_f4 + jp] = v;
+    }
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);      // ends with __syncthreads()
+    const TabView tv{tab + (threadIdx.x & (copies - 1)) * copy_f4, row_f4};
+    if ((int)threadIdx.x >= envs_per_block) return;
+
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const int e = blk * envs_per_block + threadIdx.x;
+        if (e >= n_envs) break;
+        EnvState s;
+        {
+            const double2 p = pos[e], v = vel[e];
+            const int4 q = ints[e];
+            s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
+            s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
+        }
+        int a_next = (int)actions[e];
+        for (int t = 0; t < n_steps; ++t) {
+            const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+            const int a = a_next;
+            if (t + 1 < n_steps) a_next = (int)actions[idx + (size_t)n_envs];
+            StepResult o;
+            env_step<U, true>(s, a, reward_scale, P, T, o, stats, nullptr, &tv);
+            if (obs_mode == kObsFull) {
+                float2 *dst = reinterpret_cast<float2 *>(obs_out + idx * kObsDim);
+#pragma unroll
+                for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(o.obs[2 * i], o.obs[2 * i + 1]);
+            } else if (obs_mode == kObsPose) {
+                store_pose(reinterpret_cast<PoseRec *>(obs_out) + idx, s, o.obs[2], o.obs[3]);
+            }
+            rew_out[idx] = o.reward;
+            term_out[idx] = make_flag<FlagT>(o.terminated);
+            trunc_out[idx] = make_flag<FlagT>(o.truncated);
+            if (info_out) info_out[idx] = make_int4(o.gates_passed, o.time_passed, o.next_gate, o.gate_hit | (o.lap << 1));
+        }
+        pos[e] = make_double2(s.px, s.py);
+        vel[e] = make_double2(s.vx, s.vy);
+        ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+    }
 }
 
 // Small batches: one WARP per environment, lane j = wall segment j (tracks with at most 32 segments), per-ray
@@ -870,6 +938,44 @@ int launch_rollout_t(Handle *h, int n_envs, int n_steps, double *pos, double *ve
     return 0;
 }
 
+// k_rollout_tab: table geometry, balanced block size, launch.  Returns 1 if the table does not fit in shared memory.
+template <typename ActT, typename FlagT>
+int launch_rollout_tab(Handle *h, int U, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints,
+                       const void *actions, double reward_scale, float *obs_out, float *reward_out, void *term_out,
+                       void *trunc_out, int32_t *info_out, cudaStream_t stream, int obs_mode) {
+    const int n_pairs = h->host.n_pairs;
+    const int row_f4 = (n_pairs + 7) / 8 * 8;                // rows are multiples of 128 bytes
+    const int table_bytes = (int)((h->smem_bytes + 15) / 16 * 16);
+    int copies = 8;
+    auto total = [&](int c) { return (size_t)table_bytes + 128 + (size_t)c * (kHeadings * row_f4 + 1) * 16; };
+    while (copies > 1 && total(copies) > 200 * 1024) copies >>= 1;
+    if (total(copies) > 200 * 1024) return 1;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int block = h->block > 0 ? h->block * 4 : kTabThreads;           // tuning hook (block is 0..128: x4)
+    const long long per_wave = (long long)sms * block;
+    const int rounds = (int)((n_envs + per_wave - 1) / per_wave);
+    int epb = (int)((n_envs + (long long)sms * rounds - 1) / ((long long)sms * rounds));
+    epb = (epb + 31) / 32 * 32;
+    if (epb > block) epb = block;
+    const int n_blocks = (n_envs + epb - 1) / epb;
+    const int grid = n_blocks < sms ? n_blocks : sms;
+    const size_t smem = total(copies);
+    auto launch = [&](auto kern) -> int {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, block, smem, stream>>>(
+            h->host.P, h->dev, h->d_den4, n_pairs, row_f4, copies, table_bytes, n_envs, n_steps, epb, n_blocks,
+            reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints),
+            static_cast<const ActT *>(actions), reward_scale, obs_out, reward_out, static_cast<FlagT *>(term_out),
+            static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out), h->d_stats, obs_mode);
+        CU(cudaGetLastError());
+        return 0;
+    };
+    if (U == 6) return launch(k_rollout_tab<ActT, FlagT, 6>);
+    if (U == 4) return launch(k_rollout_tab<ActT, FlagT, 4>);
+    return launch(k_rollout_tab<ActT, FlagT, 2>);
+}
+
 // Segment-loop unrolling is chosen per track (TrackParams::unroll); all variants give identical results.
 template <typename ActT, typename FlagT>
 int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints, const void *actions,
@@ -891,6 +997,15 @@ int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel,
     int U = h->force_generic ? 1 : h->host.P.unroll;
     if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
     if (h->host.P.n_seg > kMaxSeg) U = 0;                   // geometry from shared memory
+    // large launches: denominators from the shared-memory table (k_rollout_tab).  "Large" = at least two warps per
+    // scheduler on every SM and enough steps to amortise staging the table copies (147 KB per CTA on big_track).
+    if (U >= 2 && h->d_den4 && h->tab >= 0 &&
+        (h->tab == 1 || (n_envs >= 148 * 256 && (long long)n_envs * n_steps >= (1LL << 22)))) {
+        const int rc = launch_rollout_tab<ActT, FlagT>(h, U, n_envs, n_steps, pos, vel, ints, actions, reward_scale,
+                                                       obs_out, reward_out, term_out, trunc_out, info_out, stream,
+                                                       obs_mode);
+        if (rc != 1) return rc;                              // 1: the table does not fit, fall through to k_rollout
+    }
 #define ARGS h, n_envs, n_steps, pos, vel, ints, actions, reward_scale, obs_out, reward_out, term_out, trunc_out, info_out, stream, obs_mode
     if (U == 6) return launch_rollout_t<ActT, FlagT, 6>(ARGS);
     if (U == 4) return launch_rollout_t<ActT, FlagT, 4>(ARGS);
@@ -949,7 +1064,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0; h->warp_per_env = 0; h->hs = nullptr;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0; h->warp_per_env = 0; h->hs = nullptr; h->d_den4 = nullptr; h->tab = 0;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -957,7 +1072,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     DeviceGuard guard(device);
     if (!guard.ok) { delete h; return fail(CARENV_E_NOGPU, "cannot select CUDA device"); }
     const size_t b_trig64 = sizeof(D2) * kHeadings, b_acc = sizeof(D2) * kHeadings;
-    const size_t b_gates = sizeof(GateRec) * (size_t)n_gates, b_trig32 = sizeof(F2) * kHeadings;
+    const size_t b_gates = sizeof(GateRec) * (size_t)n_gates, b_trig32 = 2 * sizeof(F2) * kHeadings;   // trig32 | trig32s
     const size_t b_walls = sizeof(double) * 4 * (size_t)n_walls;
     const size_t b_segf = sizeof(SegF) * (size_t)n_walls, b_segd = sizeof(SegD) * (size_t)n_walls;
     const size_t o_acc = b_trig64, o_gates = o_acc + b_acc, o_trig32 = o_gates + b_gates, o_walls = o_trig32 + b_trig32;
@@ -966,13 +1081,16 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     // staged to shared memory: everything up to the walls, plus the segment records for big tracks
     h->smem_bytes = big ? o_segd + b_segd : o_walls + b_walls;
     if (h->smem_bytes > 200 * 1024) { delete h; return fail(CARENV_E_TRACK, "track tables do not fit in shared memory"); }
-    cudaError_t e = cudaMalloc(&h->d_blob, o_segd + b_segd);
+    const size_t o_den4 = (o_segd + b_segd + 15) / 16 * 16, b_den4 = sizeof(float) * h->host.den4.size();
+    cudaError_t e = cudaMalloc(&h->d_blob, o_den4 + b_den4 + 16);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_stats, sizeof(unsigned long long) * kNumStats);
     if (e == cudaSuccess) e = cudaMemset(h->d_stats, 0, sizeof(unsigned long long) * kNumStats);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob, h->host.trig64.data(), b_trig64, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_acc, h->host.acc64.data(), b_acc, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_gates, h->host.gates.data(), b_gates, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_trig32, h->host.trig32.data(), b_trig32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_trig32, h->host.trig32.data(), b_trig32 / 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_trig32 + b_trig32 / 2, h->host.trig32s.data(), b_trig32 / 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && b_den4) e = cudaMemcpy(h->d_blob + o_den4, h->host.den4.data(), b_den4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_walls, h->host.walls64.data(), b_walls, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_segf, h->host.segf.data(), b_segf, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_blob + o_segd, h->host.segd.data(), b_segd, cudaMemcpyHostToDevice);
@@ -985,6 +1103,8 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     h->dev.acc64 = reinterpret_cast<const D2 *>(h->d_blob + o_acc);
     h->dev.gates = reinterpret_cast<const GateRec *>(h->d_blob + o_gates);
     h->dev.trig32 = reinterpret_cast<const F2 *>(h->d_blob + o_trig32);
+    h->dev.trig32s = h->dev.trig32 + kHeadings;
+    h->d_den4 = b_den4 ? reinterpret_cast<const float4 *>(h->d_blob + o_den4) : nullptr;
     h->dev.walls64 = reinterpret_cast<const double *>(h->d_blob + o_walls);
     h->dev.segf = reinterpret_cast<const SegF *>(h->d_blob + o_segf);
     h->dev.segd = reinterpret_cast<const SegD *>(h->d_blob + o_segd);
@@ -1340,6 +1460,7 @@ int carenv_set_option(void *handle, const char *name, int value) {
         h->block = value; return 0;
     }
     if (std::string(name) == "pose_rows") { h->pose_rows = value ? 1 : 0; return 0; }
+    if (std::string(name) == "tab") { h->tab = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
     if (std::string(name) == "warp_per_env") { h->warp_per_env = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
     if (std::string(name) == "tc_tiles") {
         if (value != 0 && value != 2 && value != 4) return fail(CARENV_E_INVAL, "tc_tiles must be 0, 2 or 4");

@@ -15,14 +15,17 @@ namespace carenv {
 
 struct HostTrack {
     TrackParams P;
-    std::vector<F2> trig32;
+    std::vector<F2> trig32, trig32s;
+    std::vector<float> den4;     // [72][n_pairs][4]: seg_den of both segments of a pair (tracks the pair kernels take)
+    int n_pairs = 0;
     std::vector<D2> trig64, acc64;
     std::vector<GateRec> gates;
     std::vector<double> walls64;
     std::vector<SegF> segf;      // every segment (TrackParams only holds them up to kMaxSeg)
     std::vector<SegD> segd;
     Tables tables() const {
-        return Tables{trig32.data(), trig64.data(), acc64.data(), gates.data(), walls64.data(), segf.data(), segd.data()};
+        return Tables{trig32.data(), trig32s.data(), trig64.data(), acc64.data(), gates.data(), walls64.data(),
+                      segf.data(), segd.data()};
     }
 };
 
@@ -36,12 +39,13 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
     P.start_x = sx; P.start_y = sy;
 
     const double DEG = M_PI / 180.0;   // np.radians
-    H.trig32.resize(kHeadings); H.trig64.resize(kHeadings); H.acc64.resize(kHeadings);
+    H.trig32.resize(kHeadings); H.trig32s.resize(kHeadings); H.trig64.resize(kHeadings); H.acc64.resize(kHeadings);
     for (int k = 0; k < kHeadings; ++k) {
         const double ang = angle_deg + 5.0 * k;
         const double c = cos(ang * DEG), s = sin(ang * DEG);
         H.trig64[k] = D2{c, s};
         H.trig32[k] = F2{(float)c, (float)s};
+        H.trig32s[k] = F2{(float)c * kQScale, (float)s * kQScale};      // exact: a power of two
         H.acc64[k] = D2{c * 0.8, s * 0.8};
     }
 
@@ -56,7 +60,7 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
         const double ex = bx - ax, ey = by - ay;
         f.ex = (float)ex; f.ey = (float)ey; f.ney = -f.ey;
         f.chain_start = (j == 0 || walls[4 * j - 2] != ax || walls[4 * j - 1] != ay) ? 1 : 0;
-        H.segd[j] = SegD{fma(ex, ay, -(ey * ax)), ex, ey};
+        H.segd[j] = SegD{fma(ex, ay, -(ey * ax)) * kQScaleD, ex * kQScaleD, ey * kQScaleD};   // exact scalings
         if (n_walls <= kMaxSeg) { P.segf[j] = H.segf[j]; P.segd[j] = H.segd[j]; }
         const double len = hypot(ex, ey);
         if (len > 0)
@@ -76,11 +80,12 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
 
     // guard bands: bounds on the float32 error of q, r and the gate margin
     P.eps_q = 1.5e-3f;      // |dq| <= 6.1e-4 px for |P - pos| <= 1500 px (see wall_point)
+    P.eps_qs = P.eps_q * kQScale;
     const double rel_r = 4.0e-7 / min_sin + 3.0e-7;   // relative error of r = cross(e,d) / cross(e,A')
     P.coll_band = (float)fmax(2.0e-4, 4.0 * rel_r);
     P.tiny_d = 1.0e-2f;
     P.gate_band = 2.0e-3f;
-    P.tiny_un = 1.0e-3f;    // float64 error of cross(e, A - pos) is ~1e-10: relative error < 1e-7 above this
+    P.tiny_un = 1.0e-3f * kQScale;   // float64 error of cross(e, A - pos) is ~1e-10: relative error < 1e-7 above 1e-3
     // loop unrolling the track allows (see cast_walls)
     P.unroll = (n_walls <= kMaxSeg) ? 1 : 0;
     P.unroll4 = 1;
@@ -92,6 +97,21 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
             if (H.segf[j].chain_start && j % U != 0) ok = false;
         if (ok && P.unroll <= 1) P.unroll = U;
         if (ok && U <= 4 && P.unroll4 <= 1) P.unroll4 = U;
+    }
+
+    // denominators of the pair kernels, tabulated per heading (k_rollout_tab): exactly what wall_pair computes
+    H.n_pairs = 0;
+    H.den4.clear();
+    if (P.unroll >= 2) {
+        H.n_pairs = n_walls / 2;
+        H.den4.resize((size_t)kHeadings * H.n_pairs * 4);
+        for (int k = 0; k < kHeadings; ++k)
+            for (int jp = 0; jp < H.n_pairs; ++jp) {
+                float *d = &H.den4[((size_t)k * H.n_pairs + jp) * 4];
+                const F2 t = H.trig32s[k];
+                seg_den(H.segf[2 * jp].ex, H.segf[2 * jp].ey, t.y, t.x, d[0], d[1]);
+                seg_den(H.segf[2 * jp + 1].ex, H.segf[2 * jp + 1].ey, t.y, t.x, d[2], d[3]);
+            }
     }
 
     const Tables T = H.tables();

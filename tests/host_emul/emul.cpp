@@ -16,6 +16,9 @@ extern "C" int emul_rollout(const double *walls, int n_walls, const double *gate
     HostTrack H;
     if (build_host_track(walls, n_walls, gates, n_gates, sx, sy, angle, H) != 0) return -1;
     const Tables Tb = H.tables();
+    // unrolled == 2: the table variant of the pair path (k_rollout_tab), reading the host's den4 table directly
+    const TabView tv{reinterpret_cast<const float4 *>(H.den4.data()), H.n_pairs};
+    const bool tab = unrolled == 2 && H.n_pairs > 0 && H.P.unroll >= 2;
     if (reset_obs) for (int i = 0; i < kObsDim; ++i) reset_obs[i] = H.P.reset_obs[i];
     for (int e = env_lo; e < env_hi; ++e) {
         EnvState s;
@@ -29,7 +32,10 @@ extern "C" int emul_rollout(const double *walls, int n_walls, const double *gate
             const size_t k = (size_t)t * n_envs + e;
             StepResult o;
             const int U = H.P.n_seg > kMaxSeg ? 0 : (unrolled ? H.P.unroll : 1);
-            if (U == 0) env_step<0>(s, actions[k], reward_scale, H.P, Tb, o, stats);
+            if (tab && U == 6) env_step<6, true>(s, actions[k], reward_scale, H.P, Tb, o, stats, nullptr, &tv);
+            else if (tab && U == 4) env_step<4, true>(s, actions[k], reward_scale, H.P, Tb, o, stats, nullptr, &tv);
+            else if (tab && U == 2) env_step<2, true>(s, actions[k], reward_scale, H.P, Tb, o, stats, nullptr, &tv);
+            else if (U == 0) env_step<0>(s, actions[k], reward_scale, H.P, Tb, o, stats);
             else if (U == 6) env_step<6>(s, actions[k], reward_scale, H.P, Tb, o, stats);
             else if (U == 4) env_step<4>(s, actions[k], reward_scale, H.P, Tb, o, stats);
             else if (U == 2) env_step<2>(s, actions[k], reward_scale, H.P, Tb, o, stats);

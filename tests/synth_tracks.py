@@ -27,3 +27,27 @@ def ring_track(path, n_outer, n_inner, n_gates=12, wobble=0.08, seed_phase=0.3):
     with open(path, "w") as fh:
         json.dump(data, fh)
     return path
+
+
+def near_wall_track(path, gap_px=6.0, n_outer=10, n_inner=6):
+    """A ring track whose start pose is `gap_px` (< 10) pixels from an outer wall along ray 0, so that the very
+    first Car.update inside CarEnv.reset already sets `destroyed` (lib/car_env.py:682-686) and EVERY step
+    terminates with the -3 penalty (lib/car_env.py:745-748; `destroyed` is only cleared by reset)."""
+    ring_track(path, n_outer, n_inner)
+    with open(path) as fh:
+        data = json.load(fh)
+    W, H = 1280.0, 720.0
+    a, b = data["outer_track_points"][2], data["outer_track_points"][3]
+    ax, ay, bx, by = a[0] * W, a[1] * H, b[0] * W, b[1] * H
+    mx, my = 0.5 * (ax + bx), 0.5 * (ay + by)
+    nx, ny = -(by - ay), bx - ax                               # a normal of the wall ...
+    if nx * (0.5 * W - mx) + ny * (0.5 * H - my) < 0:          # ... turned towards the centre of the ring
+        nx, ny = -nx, -ny
+    ln = math.hypot(nx, ny)
+    nx, ny = nx / ln, ny / ln
+    sx, sy = mx + gap_px * nx, my + gap_px * ny
+    data["initial_position"] = [sx / W, sy / H]
+    data["initial_angle"] = math.degrees(math.atan2(-ny, -nx))  # ray 0 points straight at the wall
+    with open(path, "w") as fh:
+        json.dump(data, fh)
+    return path

@@ -9,7 +9,7 @@ import pytest
 
 from oracle.c_oracle import COracleVecEnv
 from tests.emul_util import emul_rollout
-from tests.parity import assert_floats_close, assert_trajectory_matches
+from tests.parity import RTOL_SYNTHETIC, assert_floats_close, assert_trajectory_matches
 
 GROUPS = ["const", "lap", "random", "fwd"]
 
@@ -62,16 +62,18 @@ def test_reward_scaling_is_float32_of_float64_product(tracks_dir):
 
 
 def test_packed_and_scalar_wall_paths_are_bit_identical(tracks_dir):
-    """The FFMA2-packed pair path (U = 2, 4) and the scalar segment loop (U = 1) perform the same IEEE
-    operations per component: observations, rewards, flags and final state must be identical bits."""
+    """The FFMA2-packed pair path (U = 2, 4, 6), its table variant (denominators read from the per-track table
+    instead of recomputed) and the scalar segment loop (U = 1) perform the same IEEE operations per component:
+    observations, rewards, flags and final state must be identical bits."""
     rng = np.random.default_rng(17)
     acts = rng.choice(9, size=(400, 256), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04]).astype(np.uint8)
     for name in ("track", "big_track"):
         path = os.path.join(tracks_dir, name + ".json")
         a, b = emul_rollout(path, acts, unrolled=True), emul_rollout(path, acts, unrolled=False)
+        c = emul_rollout(path, acts, unrolled=2)              # denominators from the per-track table (k_rollout_tab)
         for k in ("obs", "rew", "term", "trunc", "info", "state_pv", "state_i"):
-            assert np.array_equal(a[k], b[k]), (name, k)
-        assert np.array_equal(a["stats"], b["stats"])
+            assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]), (name, k)
+        assert np.array_equal(a["stats"], b["stats"]) and np.array_equal(a["stats"], c["stats"])
 
 
 @pytest.mark.parametrize("n_outer,n_inner", [(7, 5), (10, 6), (16, 12), (31, 29), (90, 80)])
@@ -88,7 +90,7 @@ def test_other_segment_counts_match_oracle(tmp_path, n_outer, n_inner):
     e = emul_rollout(path, acts)
     got = dict(obs=e["obs"], rew=e["rew"], term=e["term"], trunc=e["trunc"], gates_passed=e["info"][..., 0],
                time_passed=e["info"][..., 1], next_gate_index=e["info"][..., 2])
-    assert_trajectory_matches(got, ref, what=f"ring {n_outer}+{n_inner}")
+    assert_trajectory_matches(got, ref, what=f"ring {n_outer}+{n_inner}", rtol=RTOL_SYNTHETIC)
     assert ref["term"].sum() > 50 and ref["gates_passed"].max() > 0
 
 
@@ -140,4 +142,67 @@ def test_random_ring_tracks_match_oracle(tmp_path, seed):
     e = emul_rollout(path, acts)
     got = dict(obs=e["obs"], rew=e["rew"], term=e["term"], trunc=e["trunc"], gates_passed=e["info"][..., 0],
                time_passed=e["info"][..., 1], next_gate_index=e["info"][..., 2])
-    assert_trajectory_matches(got, ref, what=f"ring {n_outer}+{n_inner} (seed {seed})")
+    assert_trajectory_matches(got, ref, what=f"ring {n_outer}+{n_inner} (seed {seed})", rtol=RTOL_SYNTHETIC)
+
+
+def test_start_pose_inside_the_collision_distance(tmp_path):
+    """`start_destroyed` (lib/car_env.py:682-686, 745-748): the start pose is 6 px from a wall, so Car.update inside
+    reset already sets `destroyed`; every step then terminates with -3 (+0.01 when thrusting forward) and the
+    autoreset puts the car back on the same spot.  Kernel arithmetic vs the port (= the reference's behaviour,
+    see test_port_against_live_reference_when_available) and vs the C oracle."""
+    from oracle.carenv_port import PortVecEnv
+    from tests.synth_tracks import near_wall_track
+
+    path = near_wall_track(str(tmp_path / "near_wall.json"))
+    rng = np.random.default_rng(12)
+    T, N = 30, 48
+    acts = rng.integers(0, 9, size=(T, N)).astype(np.uint8)
+    e = emul_rollout(path, acts)
+    assert e["term"].all() and not e["trunc"].any() and (e["info"][..., 1] == 1).all()
+    fwd = np.isin(acts, (0, 4, 5))
+    assert np.array_equal(e["rew"], np.where(fwd, np.float32(0.01 - 3.0), np.float32(-3.0)))
+    assert np.array_equal(e["obs"], np.broadcast_to(e["reset_obs"], e["obs"].shape))
+    ora = COracleVecEnv(N, path, scan_all_gates=True)
+    obs0 = ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    assert_floats_close(np.broadcast_to(e["reset_obs"], obs0.shape), obs0, "reset obs")
+    got = dict(obs=e["obs"], rew=e["rew"], term=e["term"], trunc=e["trunc"], gates_passed=e["info"][..., 0],
+               time_passed=e["info"][..., 1], next_gate_index=e["info"][..., 2])
+    assert_trajectory_matches(got, ref, what="near-wall start")
+    port = PortVecEnv(4, path)
+    assert_floats_close(np.broadcast_to(e["reset_obs"], (4, 18)), port.reset(), "reset obs vs port")
+    for t in range(8):
+        o, r, te, tr, info = port.step(acts[t, :4])
+        assert te.all() and np.array_equal(r.astype(np.float32), e["rew"][t, :4])
+        assert np.array_equal(info["time_passed"], e["info"][t, :4, 1])
+
+
+def test_config1_shape_track_json_24_envs_1024_uniform_steps(tracks_dir):
+    """BASELINE configs[0] exactly: tracks/track.json, 24 envs x 1024 steps, i.i.d. uniform actions."""
+    path = os.path.join(tracks_dir, "track.json")
+    acts = np.random.default_rng(101).integers(0, 9, size=(1024, 24)).astype(np.uint8)
+    ora = COracleVecEnv(24, path, scan_all_gates=True)
+    ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    e = emul_rollout(path, acts)
+    got = dict(obs=e["obs"], rew=e["rew"], term=e["term"], trunc=e["trunc"], gates_passed=e["info"][..., 0],
+               time_passed=e["info"][..., 1], next_gate_index=e["info"][..., 2])
+    assert_trajectory_matches(got, ref, what="config 1")
+    assert ref["term"].sum() > 50
+
+
+@pytest.mark.parametrize("name", ["track", "big_track"])
+def test_next_gate_only_test_equals_the_full_ordered_gate_scan(tracks_dir, name):
+    """The kernel tests gate `next_gate_index` only; the reference scans every active gate in index order
+    (lib/car_env.py:394-408).  Oracle in its literal full-scan mode, forward-biased actions (many gate events)."""
+    path = os.path.join(tracks_dir, name + ".json")
+    n, T = 1024, 512
+    acts = np.random.default_rng(77).choice(9, size=(T, n), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04]).astype(np.uint8)
+    ora = COracleVecEnv(n, path, scan_all_gates=True)
+    ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    e = emul_rollout(path, acts)
+    got = dict(obs=e["obs"], rew=e["rew"], term=e["term"], trunc=e["trunc"], gates_passed=e["info"][..., 0],
+               time_passed=e["info"][..., 1], next_gate_index=e["info"][..., 2])
+    assert_trajectory_matches(got, ref, what=f"{name}, full gate scan")
+    assert (e["info"][..., 3] & 1).sum() > 2000                # gate events

@@ -97,12 +97,12 @@ def test_gae_port_bit_exact(golden_dir, tag):
 
 
 def test_port_against_live_reference_when_available(tracks_dir):
-    """In the build container the unmodified reference is mounted: replay fresh random actions through it and
-    through the port (bit-exact).  Skipped on the GPU box, where /root/reference does not exist."""
+    """Replay fresh random actions through the UNMODIFIED reference (the /root/reference mount in the build
+    container, the verified oracle/_ref copy on the GPU box) and through the port: bit-exact."""
     from oracle.ref_import import RefVecEnv, reference_available, track_path
 
     if not reference_available():
-        pytest.skip("reference tree not mounted")
+        pytest.skip("neither /root/reference nor oracle/_ref (python oracle/make_ref.py) is present")
     rng = np.random.default_rng(2024)
     for name in TRACK_NAMES:
         acts = rng.choice(9, size=(150, 3), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04])
@@ -115,3 +115,36 @@ def test_port_against_live_reference_when_available(tracks_dir):
             assert np.array_equal(te1, te2) and np.array_equal(tr1, tr2)
             assert np.array_equal(i1["gates_passed"], i2["gates_passed"])
             assert np.array_equal(i1["next_gate_index"], i2["next_gate_index"])
+
+
+def test_port_against_live_reference_start_destroyed(tmp_path):
+    """The branch the shipped tracks never take: a start pose inside the collision distance
+    (lib/car_env.py:682-686).  Unmodified reference vs port, bit-exact."""
+    from oracle.ref_import import RefVecEnv, reference_available
+    from tests.synth_tracks import near_wall_track
+
+    if not reference_available():
+        pytest.skip("neither /root/reference nor oracle/_ref is present")
+    path = near_wall_track(str(tmp_path / "near_wall.json"))
+    acts = np.random.default_rng(5).integers(0, 9, size=(12, 3))
+    ref, port = RefVecEnv(3, path), PortVecEnv(3, path)
+    assert np.array_equal(ref.reset(), port.reset())
+    for t in range(acts.shape[0]):
+        o1, r1, te1, tr1, i1 = ref.step(acts[t])
+        o2, r2, te2, tr2, i2 = port.step(acts[t])
+        assert te1.all() and np.array_equal(te1, te2) and np.array_equal(r1, r2) and np.array_equal(o1, o2)
+        assert np.array_equal(i1["final_obs"], i2["final_obs"]) and np.array_equal(i1["time_passed"], i2["time_passed"])
+
+
+def test_reference_copy_recipe_is_byte_identical(tmp_path):
+    """oracle/make_ref.py copies the hot-path files unmodified: when both the mount and the copy exist they are
+    byte-identical, and the MANIFEST hashes verify."""
+    from oracle import ref_import
+
+    copy = ref_import.reference_root(prefer_copy=True)
+    if copy is None or not copy.endswith("_ref"):
+        pytest.skip("oracle/_ref not populated")
+    assert ref_import._copy_is_intact()
+    if os.path.isfile(os.path.join(ref_import._MOUNT, "lib", "car_env.py")):
+        for rel in ("lib/car_env.py", "lib/buffer.py", "tracks/track.json", "tracks/big_track.json"):
+            assert open(os.path.join(copy, rel), "rb").read() == open(os.path.join(ref_import._MOUNT, rel), "rb").read()

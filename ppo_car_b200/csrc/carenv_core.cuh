@@ -53,27 +53,31 @@ constexpr int kTimeLimit = 1000;   // lib/car_env.py:491
 // denominators cross(e, d) and the ray-independent numerators cross(e, A - pos) are scaled alike, so that
 // r = den' / un' is unchanged bit for bit.
 constexpr float kQScale = 1125899906842624.0f;      // 2^50
+// r = 1/u of "no hit yet": its reciprocal is far above the 1000 px the reference starts its running minimum from
+// (lib/car_env.py:198), so min(1/r, 1000) is the reference's "if d < best".
+constexpr float kNoHitR = 1.0e-30f;
 constexpr double kQScaleD = 1125899906842624.0;
 
 struct F2 { float x, y; };
 struct D2 { double x, y; };
 
-// One wall segment A->B in float32 (endpoints rounded from float64; they only feed sign tests).
+// One wall segment A->B in float32 (endpoints rounded from float64; they only feed sign tests).  The layout puts
+// what a packed FFMA2 takes as ONE uniform operand next to each other: a scalar that is broadcast (bhx, ex, ahx)
+// and 8-byte aligned pairs (-y, y).  The first 16 bytes are all the table kernel needs per segment.
 struct alignas(16) SegF {
-    float bhx, bhy;        // first 16 bytes = what every segment needs: one 128-bit uniform load
-    float ney, ey;         // (-ey, ey) adjacent and 8-byte aligned: one packed operand of the den computation
-    float ex;              // B - A rounded from float64
-    int chain_start;       // 1: A is not the previous segment's B
-    float ahx, ahy;        // only read at a polyline start
+    float bhx, ex, nbhy, bhy;      // end point B: x (broadcast operand), (-y, y) (packed operand); ex = (B - A).x
+    float ney, ey, ahx;            // (-ey, ey): packed operand of the denominators; ahx: only read at a polyline start
+    int chain_start;               // 1: A is not the previous segment's B
+    float nahy, ahy, pad0, pad1;   // (-ahy, ahy)
 };
-struct SegHead { float bhx, bhy, ney, ey; };
+struct SegHead { float bhx, ex, nbhy, bhy; };
 #if defined(__CUDA_ARCH__)
 CE_HD SegHead seg_head(const SegF &f) {
     const float4 v = *reinterpret_cast<const float4 *>(&f);
     return SegHead{v.x, v.y, v.z, v.w};
 }
 #else
-CE_HD SegHead seg_head(const SegF &f) { return SegHead{f.bhx, f.bhy, f.ney, f.ey}; }
+CE_HD SegHead seg_head(const SegF &f) { return SegHead{f.bhx, f.ex, f.nbhy, f.bhy}; }
 #endif
 struct SegD { double K, ex, ey; };   // 2^50 * (cross(e, A), ex, ey):  un' = 2^50 * cross(e, A - pos) = K - (ex*py - ey*px)
 
@@ -290,22 +294,31 @@ CE_HD void integrate(EnvState &s, int thrust, int k_pre, const Tables &T) {
 // ---- the 12 ray distances and the wall-collision decision -------------------------------------
 struct WallAcc {
     float c[3], sn[3];      // 2^50 * directions of lines 0..2 (heading + 0/30/60 deg); lines 3..5 are these rotated by 90 deg
-    float phx, phy;         // float32(pos)
+    float cp[6];            // q' of the car's own position: q'(P) = cross(P, d') - cp  (see line_origin)
     float Rp[6], Rm[6];     // max of r = 1/u over hits with u > 0 (ray l) / min over hits with u < 0 (ray l+6)
     float gq[6];            // min |q'| per line  -> hit/miss guard
     float gu;               // min |un'| -> sign-of-u guard
     float qa[6];            // q' of the previous endpoint on each line
 };
 
-// q' = 2^50 q of one endpoint on the six lines.  Only the SIGN of q is used (and |q| for the guard), so the
-// endpoint is localised with a single float32 subtraction: |dq| <= 6.1e-4 px for |P - pos| <= 1500 px
-// (rounding of P, of pos, of the difference, of the two products and of the direction), below eps_q.
-CE_HD void wall_point(const WallAcc &w, float hx, float hy, float q[6]) {
-    const float x = fsub(hx, w.phx), y = fsub(hy, w.phy);
+// q'(P) = 2^50 cross(P - pos, d) is evaluated as cross(P, d') - cross(pos, d'): the wall points P are per-track
+// constants (uniform operands of the FMA), so an endpoint costs two FMAs per line and nothing else.  Only the SIGN
+// of q is used (and |q| for the guard).  Error bound for coordinates <= 1280 x 720 and |P - pos| <= 1469 px:
+// float32(P) 6.1e-5 + 3.1e-5, float32(pos) the same, direction 1.2e-4, the product and the two sums of cp and of
+// the inner FMA 3.1e-5 + 6.1e-5 + 1.2e-4, the final rounding 6.1e-5: |dq| <= 5.7e-4 px < eps_q = 1.5e-3.
+CE_HD void line_origin(WallAcc &w, double px, double py) {
+    const float phx = (float)px, phy = (float)py;
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
-        q[l] = ffma(x, w.sn[l], -fmul(y, w.c[l]));        // cross(P', d_l)
-        q[l + 3] = ffma(x, w.c[l], fmul(y, w.sn[l]));     // cross(P', rot90 d_l) = dot(P', d_l)
+        w.cp[l] = ffma(phx, w.sn[l], -fmul(phy, w.c[l]));
+        w.cp[l + 3] = ffma(phx, w.c[l], fmul(phy, w.sn[l]));
+    }
+}
+CE_HD void wall_point(const WallAcc &w, float hx, float hy, float q[6]) {
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        q[l] = ffma(hx, w.sn[l], ffma(-hy, w.c[l], -w.cp[l]));          // cross(P', d_l)
+        q[l + 3] = ffma(hx, w.c[l], ffma(hy, w.sn[l], -w.cp[l + 3]));   // cross(P', rot90 d_l) = dot(P', d_l)
     }
 }
 
@@ -361,7 +374,7 @@ CE_HD void wall_segment(WallAcc &w, const SegF &f, const SegD &g, double px, dou
 // in wall_segment, so both paths give bit-identical results.
 struct WallAcc2 {
     P2 S[3];                // S_l = 2^50 (s_l, c_l); its half-swap (c_l, s_l) is a free operand modifier
-    float phx, phy;         // float32(pos)
+    P2 CP[3];               // (cp_l, cp_{l+3}): q' of the car's own position (line_origin2)
     float Rp[6], Rm[6], gq[6], gu;
     P2 QA[3];               // (q'_l, q'_{l+3}) of the previous endpoint
 };
@@ -379,16 +392,22 @@ struct TabView {
     int row_f4;             // float4 per row
 };
 
-// (q_l, q_{l+3}) = x*(s_l, c_l) + (-y, y)*(c_l, s_l): only S_l is kept in registers (keeping the rotated
-// pair (-c_l, s_l) as well made the compiler rebuild it in every loop iteration).
-CE_HD void wall_point2(const WallAcc2 &w, float hx, float hy, P2 Q[3]) {
-    const float x = fsub(hx, w.phx), y = fsub(hy, w.phy), yn = fsub(w.phy, hy);   // yn == -y exactly
+// (q_l, q_{l+3}) = hx*(s_l, c_l) + ((-hy, hy)*(c_l, s_l) - (cp_l, cp_{l+3})): two FFMA2 whose wall-point operands
+// come straight from uniform registers — the same IEEE operations per component as wall_point.
+CE_HD void line_origin2(WallAcc2 &w, double px, double py) {
+    const float phx = (float)px, phy = (float)py, nphy = -phy;
 #pragma unroll
-    for (int l = 0; l < 3; ++l) Q[l] = pfma(p2(x, x), w.S[l], pmul(p2(yn, y), p2(w.S[l].y, w.S[l].x)));
+    for (int l = 0; l < 3; ++l)
+        w.CP[l] = pfma(p2(phx, phx), w.S[l], pmul(p2(nphy, phy), p2(w.S[l].y, w.S[l].x)));
+}
+CE_HD void wall_point2(const WallAcc2 &w, float hx, float nhy, float hy, P2 Q[3]) {
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+        Q[l] = pfma(p2(hx, hx), w.S[l], pfma(p2(nhy, hy), p2(w.S[l].y, w.S[l].x), p2(-w.CP[l].x, -w.CP[l].y)));
 }
 
 CE_HD void wall_chain_start2(WallAcc2 &w, const SegF &f) {
-    wall_point2(w, f.ahx, f.ahy, w.QA);
+    wall_point2(w, f.ahx, f.nahy, f.ahy, w.QA);
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
         w.gq[l] = fminf(w.gq[l], fabsf(w.QA[l].x));
@@ -402,9 +421,9 @@ template <bool TAB>
 CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1, const SegD &g1, double px,
                      double py, const float4 *const *tb = nullptr, int jp = 0) {
     P2 QB0[3], QB1[3];
-    const SegHead h0 = seg_head(f0), h1 = seg_head(f1);     // bhx, bhy, -ey, ey: one 128-bit uniform load each
-    wall_point2(w, h0.bhx, h0.bhy, QB0);
-    wall_point2(w, h1.bhx, h1.bhy, QB1);
+    const SegHead h0 = seg_head(f0), h1 = seg_head(f1);     // bhx, ex, -bhy, bhy: one 128-bit uniform load each
+    wall_point2(w, h0.bhx, h0.nbhy, h0.bhy, QB0);
+    wall_point2(w, h1.bhx, h1.nbhy, h1.bhy, QB1);
     const float un0 = (float)dfma(g0.ey, px, dfma(-g0.ex, py, g0.K));
     const float un1 = (float)dfma(g1.ey, px, dfma(-g1.ex, py, g1.K));
     const float inv0 = frcp(un0), inv1 = frcp(un1);
@@ -417,8 +436,8 @@ CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1
             D0 = p2(t.x, t.y); D1 = p2(t.z, t.w);
         } else {
             const P2 SW = p2(w.S[l].y, w.S[l].x);
-            D0 = pfma(p2(f0.ex, f0.ex), w.S[l], pmul(p2(h0.ney, h0.ey), SW));
-            D1 = pfma(p2(f1.ex, f1.ex), w.S[l], pmul(p2(h1.ney, h1.ey), SW));
+            D0 = pfma(p2(h0.ex, h0.ex), w.S[l], pmul(p2(f0.ney, f0.ey), SW));
+            D1 = pfma(p2(h1.ex, h1.ex), w.S[l], pmul(p2(f1.ney, f1.ey), SW));
         }
         const P2 R0 = pmul(D0, p2(inv0, inv0)), R1 = pmul(D1, p2(inv1, inv1));
         const P2 H0 = pmul(R0, p2(sat_mul(w.QA[l].x, -QB0[l].x), sat_mul(w.QA[l].y, -QB0[l].y)));
@@ -448,14 +467,14 @@ __device__ __forceinline__ float warp_min_pos(float v) {
 }
 __device__ __forceinline__ void cast_walls_warp(const EnvState &s, const Tables &T, const WarpSeg &ws, float Rp[6],
                                                 float Rm[6], float gq[6], float &gu) {
-    const float R0 = 1.0e-3f;
+    const float R0 = kNoHitR;
     WallAcc w;
-    w.phx = (float)s.px; w.phy = (float)s.py;
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
         const F2 d = T.trig32s[wrap72(s.k + 6 * l)];
         w.c[l] = d.x; w.sn[l] = d.y;
     }
+    line_origin(w, s.px, s.py);
     float qa[6], qb[6];
     wall_point(w, ws.f.ahx, ws.f.ahy, qa);
     wall_point(w, ws.f.bhx, ws.f.bhy, qb);
@@ -493,7 +512,7 @@ __device__ __forceinline__ void cast_walls_warp(const EnvState &s, const Tables 
 template <int U, bool TAB = false>
 CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, float dist[kNumRays],
                       unsigned long long *stats, const WarpSeg *ws = nullptr, const TabView *tv = nullptr) {
-    const float R0 = 1.0e-3f;           // 1/1000: "no hit" (lib/car_env.py:198)
+    const float R0 = kNoHitR;
     float Rp[6], Rm[6], gq[6], gu;
     if (U == kWarpPerEnv) {
 #if defined(__CUDA_ARCH__)
@@ -505,7 +524,6 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
 #endif
     } else if (U > 1) {
         WallAcc2 w;
-        w.phx = (float)s.px; w.phy = (float)s.py;
         const float4 *tb[3] = {nullptr, nullptr, nullptr};
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
@@ -515,6 +533,7 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
             w.QA[l] = p2(0.0f, 0.0f);
             if (TAB) tb[l] = tv->base + kl * tv->row_f4;
         }
+        line_origin2(w, s.px, s.py);
 #pragma unroll
         for (int l = 0; l < 6; ++l) { w.Rp[l] = R0; w.Rm[l] = -R0; w.gq[l] = 1.0e30f; }
         w.gu = 1.0e30f;
@@ -531,12 +550,12 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
         gu = w.gu;
     } else {
         WallAcc w;
-        w.phx = (float)s.px; w.phy = (float)s.py;
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             const F2 d = T.trig32s[wrap72(s.k + 6 * l)];
             w.c[l] = d.x; w.sn[l] = d.y;
         }
+        line_origin(w, s.px, s.py);
 #pragma unroll
         for (int l = 0; l < 6; ++l) { w.Rp[l] = R0; w.Rm[l] = -R0; w.gq[l] = 1.0e30f; w.qa[l] = 0.0f; }
         w.gu = 1.0e30f;
@@ -575,8 +594,8 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
     bool destroyed = card_hi > r_coll;
 #pragma unroll
     for (int l = 0; l < 6; ++l) {
-        dist[l] = Rp[l] > R0 ? frcp(Rp[l]) : 1000.0f;
-        dist[l + 6] = Rm[l] < -R0 ? -frcp(Rm[l]) : 1000.0f;
+        dist[l] = fminf(frcp(Rp[l]), 1000.0f);          // "if d < best" from best = 1000.0 (lib/car_env.py:198-207)
+        dist[l + 6] = fminf(-frcp(Rm[l]), 1000.0f);
     }
     const bool careful = (gu < P.tiny_un) || (g_all < P.eps_qs) || (r_all > r_tiny) || (band_lo < r_band);
     if (careful) {
@@ -650,13 +669,21 @@ CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackPar
     o.reward = (float)dmul(reward, reward_scale);
     o.gates_passed = s.passed; o.time_passed = s.t; o.next_gate = s.next_gate;
 
-    if (o.terminated | o.truncated) {
-        s.px = P.start_x; s.py = P.start_y; s.vx = 0.0; s.vy = 0.0;
-        s.k = 0; s.t = 0; s.next_gate = 0; s.passed = 0;
+    // Same-step autoreset.  The live observation is formed for every lane; the reset (state overwrite + the
+    // constant reset observation, ~40 select instructions) sits behind a warp vote: an episode ends in about 0.4 %
+    // of env-steps, i.e. seven of eight warp-steps skip it with one uniform branch.
+    pose_observation(s, (float)dmul(s.vx, 0.1), (float)dmul(s.vy, 0.1), dist, T, o.obs);
+    const bool done = (o.terminated | o.truncated) != 0;
+#if defined(__CUDA_ARCH__)
+    if (__any_sync(__activemask(), done))
+#endif
+    {
+        if (done) {
+            s.px = P.start_x; s.py = P.start_y; s.vx = 0.0; s.vy = 0.0;
+            s.k = 0; s.t = 0; s.next_gate = 0; s.passed = 0;
 #pragma unroll
-        for (int i = 0; i < kObsDim; ++i) o.obs[i] = P.reset_obs[i];
-    } else {
-        pose_observation(s, (float)dmul(s.vx, 0.1), (float)dmul(s.vy, 0.1), dist, T, o.obs);
+            for (int i = 0; i < kObsDim; ++i) o.obs[i] = P.reset_obs[i];
+        }
     }
 }
 

@@ -169,10 +169,10 @@ __device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, int
     const SegF *s_segf = nullptr;
     const SegD *s_segd = nullptr;
     if (n_seg > kMaxSeg) {                                  // big track: the segment records live in shared memory too
-        static_assert(sizeof(SegF) == 32 && sizeof(SegD) == 24, "staging below copies 4 / 3 doubles per record");
-        double *d4 = s_walls + 4 * n_seg, *d5 = d4 + 4 * n_seg;            // SegF = 4 doubles, SegD = 3 doubles
+        static_assert(sizeof(SegF) == 48 && sizeof(SegD) == 24, "staging below copies 6 / 3 doubles per record");
+        double *d4 = s_walls + 4 * n_seg, *d5 = d4 + 6 * n_seg;            // SegF = 6 doubles, SegD = 3 doubles
         const double *g4 = reinterpret_cast<const double *>(G.segf), *g5 = reinterpret_cast<const double *>(G.segd);
-        for (int i = threadIdx.x; i < 4 * n_seg; i += blockDim.x) d4[i] = g4[i];
+        for (int i = threadIdx.x; i < 6 * n_seg; i += blockDim.x) d4[i] = g4[i];
         for (int i = threadIdx.x; i < 3 * n_seg; i += blockDim.x) d5[i] = g5[i];
         s_segf = reinterpret_cast<const SegF *>(d4);
         s_segd = reinterpret_cast<const SegD *>(d5);
@@ -274,7 +274,10 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
 // 512 threads per SM owns the table copies (72 headings x n_pairs x 16 B, x 8 skewed copies = 147 KB on big_track)
 // and walks over blocks of `envs_per_block` environments; the block size is chosen on the host so that every SM
 // gets the same number of blocks (no partial last wave: 131,072 envs are 2 x 148 blocks of 443).
-constexpr int kTabThreads = 512;
+#ifndef CARENV_TAB_THREADS
+#define CARENV_TAB_THREADS 512
+#endif
+constexpr int kTabThreads = CARENV_TAB_THREADS;
 template <typename ActT, typename FlagT, int U>
 __global__ void __launch_bounds__(kTabThreads, 1)
 k_rollout_tab(const __grid_constant__ TrackParams P, const Tables G, const float4 *__restrict__ den4, int n_pairs,

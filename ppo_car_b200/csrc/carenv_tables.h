@@ -56,7 +56,9 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
     for (int j = 0; j < n_walls; ++j) {
         const double ax = walls[4 * j], ay = walls[4 * j + 1], bx = walls[4 * j + 2], by = walls[4 * j + 3];
         SegF &f = H.segf[j];
-        f.ahx = (float)ax; f.ahy = (float)ay; f.bhx = (float)bx; f.bhy = (float)by;
+        memset(&f, 0, sizeof(f));
+        f.ahx = (float)ax; f.ahy = (float)ay; f.nahy = -f.ahy;
+        f.bhx = (float)bx; f.bhy = (float)by; f.nbhy = -f.bhy;
         const double ex = bx - ax, ey = by - ay;
         f.ex = (float)ex; f.ey = (float)ey; f.ney = -f.ey;
         f.chain_start = (j == 0 || walls[4 * j - 2] != ax || walls[4 * j - 1] != ay) ? 1 : 0;
@@ -79,7 +81,7 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
     }
 
     // guard bands: bounds on the float32 error of q, r and the gate margin
-    P.eps_q = 1.5e-3f;      // |dq| <= 6.1e-4 px for |P - pos| <= 1500 px (see wall_point)
+    P.eps_q = 1.5e-3f;      // |dq| <= 5.7e-4 px for coordinates within 1280 x 720 (see wall_point)
     P.eps_qs = P.eps_q * kQScale;
     const double rel_r = 4.0e-7 / min_sin + 3.0e-7;   // relative error of r = cross(e,d) / cross(e,A')
     P.coll_band = (float)fmax(2.0e-4, 4.0 * rel_r);

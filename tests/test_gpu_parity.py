@@ -483,3 +483,162 @@ def test_warp_per_env_kernel_is_bit_identical_to_thread_per_env(golden_dir, trac
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
     assert a[5] == b[5]                                       # the float64 fallback ran equally often
     assert int(a[0]["terminated"].sum()) > n and int(((a[4]["info"]["events"] >> 1) & 1).sum()) == 1
+
+
+def test_start_pose_inside_the_collision_distance_on_gpu(tmp_path):
+    """`start_destroyed` (lib/car_env.py:682-686, 745-748): start pose 6 px from a wall — every step terminates with
+    -3 (+0.01 when thrusting forward), time_passed is always 1, every observation is the reset observation."""
+    from tests.synth_tracks import near_wall_track
+
+    path = near_wall_track(str(tmp_path / "near_wall.json"))
+    T, n = 40, 300
+    acts = np.random.default_rng(12).integers(0, 9, size=(T, n)).astype(np.uint8)
+    ora = COracleVecEnv(n, path, scan_all_gates=True)
+    obs0_ref = ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    assert ref["term"].all()
+    for mode in (-1, 1):                                         # thread-per-env and warp-per-env kernels
+        env = ppo_car_b200.VecCarEnv(n, path)
+        env.set_option("warp_per_env", mode)
+        obs0, _ = env.reset()
+        assert_floats_close(obs0.cpu().numpy(), obs0_ref, "reset obs", rtol=RTOL_SYNTHETIC)
+        out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
+        assert_trajectory_matches(_gpu_traj(out), ref, what="near-wall ring start", rtol=RTOL_SYNTHETIC)
+        assert bool(out["terminated"].all()) and int(out["info"]["time_passed"].max()) == 1
+        # step() path too
+        o, r, te, tr, info = env.step(torch.from_numpy(acts[0].astype(np.int64)).cuda())
+        assert bool(te.all()) and torch.equal(o, obs0.expand_as(o))
+
+
+def test_scale_config_full_integer_traces_on_all_eight_shards(tracks_dir):
+    """BASELINE config 4 (1,048,576 envs, the bench workload, bench.py's action stream): for EACH of the eight
+    shard_range shards a 16,384-env slice x 256 steps is compared with the float64 oracle — every terminated /
+    truncated / gates_passed / time_passed / next_gate_index element and every reward (33.5 M env-steps in all),
+    observations on a 1,024-env sub-slice of every shard.  Each shard runs as its own VecCarEnv of 131,072 envs,
+    i.e. exactly what rank r of an 8-GPU run computes (k_rollout_tab with 2 x 148 balanced blocks)."""
+    from ppo_car_b200.shard import shard_range
+
+    path = os.path.join(tracks_dir, "big_track.json")
+    total, T, S, SO = 1_048_576, 256, 16_384, 1_024
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    acts = torch.randint(0, 9, (T, total), generator=gen, device="cuda", dtype=torch.uint8)
+    n_term = 0
+    for rank in range(8):
+        lo, hi = shard_range(total, 8, rank)
+        a = acts[:, lo:hi].contiguous()
+        env = ppo_car_b200.VecCarEnv(hi - lo, path)
+        env.reset()
+        out = env.rollout(a, store_info=True)
+        off = (rank * 14_321) % (hi - lo - S)                   # a different place in every shard
+        sl = slice(off, off + S)
+        ora = COracleVecEnv(S, path, scan_all_gates=False)
+        ora.reset()
+        ref = ora.rollout(a[:, sl].cpu().numpy(), want=("rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+        assert np.array_equal(out["terminated"][:, sl].cpu().numpy(), ref["term"]), rank
+        assert np.array_equal(out["truncated"][:, sl].cpu().numpy(), ref["trunc"]), rank
+        for k in ("gates_passed", "time_passed", "next_gate_index"):
+            assert np.array_equal(out["info"][k][:, sl].cpu().numpy(), ref[k]), (rank, k)
+        assert np.array_equal(out["reward"][:, sl].cpu().numpy(), ref["rew"].astype(np.float32)), rank
+        ora = COracleVecEnv(SO, path, scan_all_gates=False)
+        ora.reset()
+        ref_o = ora.rollout(a[:, off:off + SO].cpu().numpy(), want=("obs",))
+        assert_floats_close(out["obs"][:, off:off + SO].cpu().numpy(), ref_o["obs"], f"obs, shard {rank}")
+        n_term += int(ref["term"].sum())
+        del env, out
+    assert n_term > 50_000
+
+
+def test_config1_shape_track_json_24_envs_1024_uniform_steps_on_gpu(tracks_dir):
+    """BASELINE configs[0] exactly (tracks/track.json, 24 envs x 1024 steps, i.i.d. uniform actions), oracle in its
+    literal full-gate-scan mode; runs the warp-per-environment kernel (the one 24 envs get) and k_rollout."""
+    path = os.path.join(tracks_dir, "track.json")
+    acts = np.random.default_rng(101).integers(0, 9, size=(1024, 24)).astype(np.uint8)
+    ora = COracleVecEnv(24, path, scan_all_gates=True)
+    ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    for mode in (0, -1):
+        env = ppo_car_b200.VecCarEnv(24, path)
+        env.set_option("warp_per_env", mode)
+        env.reset()
+        out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
+        assert_trajectory_matches(_gpu_traj(out), ref, what=f"config 1 (warp_per_env={mode})")
+
+
+@pytest.mark.parametrize("name", ["track", "big_track"])
+def test_full_ordered_gate_scan_oracle_4096_envs(tracks_dir, name):
+    """The reference scans every active gate in index order (lib/car_env.py:394-408); the kernel tests gate
+    next_gate_index only.  4,096 envs x 768 forward-biased steps against the oracle in literal full-scan mode."""
+    path = os.path.join(tracks_dir, name + ".json")
+    n, T = 4096, 768
+    acts = np.random.default_rng(78).choice(9, size=(T, n), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04]).astype(np.uint8)
+    ora = COracleVecEnv(n, path, scan_all_gates=True)
+    ora.reset()
+    ref = ora.rollout(acts, want=("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index"))
+    env = ppo_car_b200.VecCarEnv(n, path)
+    env.reset()
+    out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
+    assert_trajectory_matches(_gpu_traj(out), ref, what=f"{name}, full gate scan")
+    assert int((out["info"]["events"] & 1).sum()) > 10_000
+
+
+@pytest.mark.parametrize("name", ["track", "big_track"])
+def test_table_kernel_is_bit_identical_to_the_arithmetic_kernel(tracks_dir, name):
+    """k_rollout_tab (denominators from the shared-memory table, 512-thread CTAs walking balanced env blocks) and
+    k_rollout (denominators recomputed) give the same bits: ragged env counts, several blocks per CTA, pose rows."""
+    path = os.path.join(tracks_dir, name + ".json")
+    T = 96
+    for n in (40_003, 131_072, 200_003):
+        g = torch.Generator(device="cuda").manual_seed(n)
+        acts = torch.randint(0, 9, (T, n), generator=g, device="cuda", dtype=torch.uint8)
+        outs = {}
+        for mode in (1, -1):
+            env = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1)
+            env.set_option("tab", mode)
+            env.reset()
+            out = env.rollout(acts, store_info=True)
+            poses = env.rollout(acts[:8], store_poses=True)["poses"]
+            outs[mode] = (out, poses, env.pos.clone(), env.vel.clone(), env.ints.clone(), env.slow_path_counts())
+        a, b = outs[1], outs[-1]
+        for k in ("obs", "reward", "terminated", "truncated"):
+            assert torch.equal(a[0][k], b[0][k]), (n, k)
+        for k in ("gates_passed", "time_passed", "next_gate_index", "events"):
+            assert torch.equal(a[0]["info"][k], b[0]["info"][k]), (n, k)
+        assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+        assert a[5] == b[5]
+
+
+def test_cuda_path_against_the_unmodified_reference(tracks_dir, tmp_path):
+    """The CUDA path against the reference's OWN code (lib/car_env.py, unmodified: the /root/reference mount in the
+    build container, the verified oracle/_ref copy on the GPU box) with gymnasium's same-step autoreset emulated:
+    both shipped tracks and the start_destroyed track.  Integers bit-exact, rewards float32(float64 reward),
+    observations 1e-5 relative."""
+    from oracle.ref_import import RefVecEnv, reference_available, track_path
+    from tests.synth_tracks import near_wall_track
+
+    if not reference_available():
+        pytest.skip("neither /root/reference nor oracle/_ref (python oracle/make_ref.py) is present")
+    rng = np.random.default_rng(31)
+    cases = [("track", track_path("track.json"), os.path.join(tracks_dir, "track.json"), 240),
+             ("big_track", track_path("big_track.json"), os.path.join(tracks_dir, "big_track.json"), 240)]
+    nw = near_wall_track(str(tmp_path / "near_wall.json"))
+    cases.append(("near_wall", nw, nw, 12))
+    n = 6
+    for name, ref_path, our_path, T in cases:
+        acts = rng.choice(9, size=(T, n), p=[.3, .02, .1, .1, .2, .2, .02, .02, .04]).astype(np.uint8)
+        acts[:, 0] = 0                                          # one env at full throttle: gates, then a crash
+        ref = RefVecEnv(n, ref_path)
+        obs0 = ref.reset()
+        rec = {k: [] for k in ("obs", "rew", "term", "trunc", "gates_passed", "time_passed", "next_gate_index")}
+        for t in range(T):
+            o, r, te, tr, info = ref.step(acts[t])
+            for k, v in (("obs", o), ("rew", r), ("term", te), ("trunc", tr), ("gates_passed", info["gates_passed"]),
+                         ("time_passed", info["time_passed"]), ("next_gate_index", info["next_gate_index"])):
+                rec[k].append(np.array(v))
+        rec = {k: np.stack(v) for k, v in rec.items()}
+        env = ppo_car_b200.VecCarEnv(n, our_path)
+        g0, _ = env.reset()
+        tol = RTOL_SYNTHETIC if name == "near_wall" else 1e-5
+        assert_floats_close(g0.cpu().numpy(), obs0, f"{name}: reset obs vs reference", rtol=tol)
+        out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
+        assert_trajectory_matches(_gpu_traj(out), rec, what=f"{name} vs unmodified reference", rtol=tol)
+        assert rec["term"].sum() > 0

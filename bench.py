@@ -2,7 +2,7 @@
 """bench.py — CarEnv env-steps/sec (BASELINE.json metric) on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repository's CUDA path
-    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU path (oracle port)
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's own CPU implementation
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (config.workload): BASELINE.json configs[3] — tracks/big_track.json, 1,048,576
@@ -17,14 +17,22 @@ compete for the FP64/XU pipes until they drift apart, benchmarks/sweep_launch.py
 such as 8 x 32 measure 2-18 % less, depending on the shard size).
 
   value     env-steps/s with actions already resident in HBM (device timed, CUDA events, max over ranks)
-  e2e       env-steps/s through the reference-facing API VecCarEnv.step(numpy actions) -> numpy
-            results: host->device copy of the actions and device->host copy of obs/reward/flags/info
-            from/to pinned memory inside the timed region, every step
+  e2e       env-steps/s through the reference-facing API VecCarEnv.step(numpy int64 actions) -> numpy
+            results in the reference's dtypes (float32 obs, float64 rewards, bool flags, int info):
+            host->device copy of the actions and device->host copy of observation + one 16-byte
+            record per env from/to pinned memory inside the timed region, every step; `bound_gbs` is
+            the pinned device->host rate all ranks reach copying at the same time, measured in the
+            same run (the PCIe ceiling of this path)
   roofline  the step kernel against the FP32 pipe (5,286 algorithmic flop per env-step on
             big_track; nominal peak 148 SM x 128 lanes x 2 x sm_max_mhz, and an FFMA probe measured in
             the same run) plus its algorithmic HBM bytes against MEASURED_PEAKS.json
-  cpu_baseline  the oracle port (a Python restatement of lib/car_env.py, bit-exact against the
-            reference's golden trajectories) on the host cores, on a bounded sample
+  cpu_baseline  the UNMODIFIED reference CarEnv (oracle/_ref: lib/car_env.py copied byte for byte by
+            oracle/make_ref.py, imported through two inert stubs for gymnasium / pygame) on the host
+            cores, one process per core, on a bounded sample; kind "reference".  The oracle port's rate
+            is reported beside it (`port_value`).  Without oracle/_ref: the port, kind "port".
+  configs   BASELINE.json's other configurations, measured after the timed region on rank 0:
+            config 2 (24 envs x 1024 steps), config 3 (65,536 envs x 1024 steps rollout + GAE) and, at
+            --gpus 8, config 5 (PPO loop, 262,144 envs, fused rollout + fused update + NCCL all-reduce)
 """
 from __future__ import annotations
 
@@ -50,17 +58,27 @@ STATE_BYTES = 48
 METRIC = "CarEnv env-steps/sec"
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+# ----------------------------------------------------------------------------- CPU baseline
+# Workers run either the UNMODIFIED reference CarEnv (oracle/_ref, kind "reference") or the oracle port (kind "port").
 _W_ENV = None
+_W_KIND = None
 
 
-def _w_init(track_path):
-    global _W_ENV
+def _w_init(track_path, kind):
+    global _W_ENV, _W_KIND
     sys.path.insert(0, ROOT)
-    from oracle.carenv_port import PortCarEnv
+    _W_KIND = kind
+    if kind == "reference":
+        from oracle.ref_import import import_reference
 
-    _W_ENV = PortCarEnv(track_path)
-    _W_ENV.reset()
+        CarEnv, _ = import_reference()
+        _W_ENV = CarEnv(track_path=track_path)
+        _W_ENV.reset(options={"track_path": track_path})
+    else:
+        from oracle.carenv_port import PortCarEnv
+
+        _W_ENV = PortCarEnv(track_path)
+        _W_ENV.reset()
 
 
 def _w_run(args):
@@ -73,18 +91,31 @@ def _w_run(args):
     for a in acts:
         _, _, te, tr, _ = env.step(int(a))
         if te or tr:
-            env.reset()                       # same-step autoreset
+            env.reset()                       # same-step autoreset (gymnasium AsyncVectorEnv worker)
     return n_steps
 
 
-class CpuPortPool:
-    """The reference's CPU path as restated by oracle/carenv_port.py, one process per host core."""
+def reference_kind_and_track():
+    """("reference", path inside oracle/_ref) when the unmodified reference files travelled with the repo, else
+    ("port", the package's copy of the track)."""
+    import ppo_car_b200.track as trk
+    from oracle import ref_import
 
-    def __init__(self, track_path, cores=None):
+    root = ref_import.reference_root(prefer_copy=True)
+    if root is not None:
+        return "reference", os.path.join(root, "tracks", TRACK + ".json")
+    return "port", trk.builtin_track(TRACK)
+
+
+class CpuPool:
+    """The reference's CPU path, one process per host core (what AsyncVectorEnv does, minus the pipes)."""
+
+    def __init__(self, track_path, kind, cores=None):
         import multiprocessing as mp
 
+        self.kind = kind
         self.cores = cores or min(os.cpu_count() or 1, 128)
-        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_w_init, initargs=(track_path,))
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_w_init, initargs=(track_path, kind))
         self.seed = 0
 
     def run(self, steps_per_env):
@@ -99,18 +130,33 @@ class CpuPortPool:
         self.pool.join()
 
 
-def cpu_baseline(track_path, target_seconds=12.0):
-    pool = CpuPortPool(track_path)
+def _timed_sample(kind, path, target_seconds):
+    pool = CpuPool(path, kind)
     try:
-        pool.run(16)                                           # warm-up / calibration
-        n, dt = pool.run(64)
-        per_env = max(64, int(64 * target_seconds / max(dt, 1e-3)))
+        pool.run(8)                                            # warm-up / calibration
+        n, dt = pool.run(24)
+        per_env = max(24, int(24 * target_seconds / max(dt, 1e-3)))
         n, dt = pool.run(per_env)
     finally:
         pool.close()
-    return {"value": n / dt, "unit": "env-steps/s", "cores": pool.cores, "kind": "port",
-            "sample": f"{pool.cores} envs x {per_env} steps, big_track.json, uniform random actions, "
-                      f"oracle/carenv_port.py (Python restatement of lib/car_env.py), one process per core, {dt:.1f} s"}
+    return n / dt, pool.cores, per_env, dt
+
+
+def cpu_baseline(target_seconds=12.0):
+    import ppo_car_b200.track as trk
+
+    kind, path = reference_kind_and_track()
+    val, cores, per_env, dt = _timed_sample(kind, path, target_seconds)
+    what = ("the UNMODIFIED reference lib/car_env.py (oracle/_ref, stub gymnasium / pygame), CarEnv.step + reset on done"
+            if kind == "reference" else "oracle/carenv_port.py (Python restatement of lib/car_env.py)")
+    out = {"value": val, "unit": "env-steps/s", "cores": cores, "kind": kind,
+           "sample": f"{cores} envs x {per_env} steps, big_track.json, uniform random actions, {what}, "
+                     f"one process per core, {dt:.1f} s"}
+    if kind == "reference":                                    # the port beside it (a faster restatement)
+        pval, _, pper, pdt = _timed_sample("port", trk.builtin_track(TRACK), 4.0)
+        out["port_value"] = pval
+        out["port_sample"] = f"{cores} envs x {pper} steps, oracle/carenv_port.py, {pdt:.1f} s"
+    return out
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -162,11 +208,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import ppo_car_b200.track as trk
-
-    path = trk.builtin_track(TRACK)
-    pool = CpuPortPool(path)
-    per_env = 96                                             # env-steps per worker per timed "step"
+    kind, path = reference_kind_and_track()
+    pool = CpuPool(path, kind)
+    per_env = 32 if kind == "reference" else 96              # env-steps per worker per timed "step" (~0.15 s)
     try:
         for _ in range(max(args.warmup, 1)):
             pool.run(per_env)
@@ -178,15 +222,18 @@ def run_reference(args):
     finally:
         pool.close()
     val = n_tot / t_tot
-    sample = (f"{pool.cores} envs x {per_env} env-steps per step, big_track.json, uniform random actions, "
-              "oracle/carenv_port.py (Python restatement of lib/car_env.py; the reference is pure Python and "
-              "cannot travel to the GPU box), one process per host core")
+    what = ("the UNMODIFIED reference lib/car_env.py from oracle/_ref (byte-for-byte copy made by oracle/make_ref.py, "
+            "imported through inert gymnasium / pygame stubs): CarEnv.step, CarEnv.reset on done"
+            if kind == "reference" else
+            "oracle/carenv_port.py (Python restatement of lib/car_env.py; oracle/_ref is absent on this box)")
+    sample = (f"{pool.cores} envs x {per_env} env-steps per step, big_track.json, uniform random actions, {what}, "
+              "one process per host core")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"tracks/{TRACK}.json, uniform random actions, same-step autoreset; "
                                    f"bounded sample of the {TOTAL_ENVS}-env workload: {sample}"},
-            "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": pool.cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": pool.cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -194,6 +241,82 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- our arm
+def kernel_source_hash():
+    import hashlib
+
+    hsh = hashlib.sha256()
+    d = os.path.join(ROOT, "ppo_car_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        hsh.update(open(os.path.join(d, f), "rb").read())
+    return hsh.hexdigest()
+
+
+def other_configs(dev, world):
+    """BASELINE.json configs 2 and 3 on this rank's GPU (rank 0, after the timed region), CUDA-event timed."""
+    import torch
+
+    import ppo_car_b200
+
+    track = ppo_car_b200.builtin_track(TRACK)
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+        return ms[len(ms) // 2]
+
+    # config 2: 24 envs x 1024 steps (README training shape): warp-per-environment kernel, one launch
+    g = torch.Generator(device=dev).manual_seed(2)
+    env = ppo_car_b200.VecCarEnv(24, track, device=dev)
+    env.reset()
+    a = torch.randint(0, 9, (1024, 24), generator=g, device=dev, dtype=torch.uint8)
+    ms = timed(lambda: env.rollout(a), 10)
+    out["config2"] = {"workload": "big_track.json, 24 envs x 1024 steps, one launch (k_rollout_warp)", "ms": ms,
+                      "env_steps_per_s": 24 * 1024 / (ms * 1e-3), "us_per_step": ms * 1e3 / 1024}
+    del env
+    # config 3: 65,536 envs x 1024 steps rollout (obs 4.8 GB written) + GAE over the [1024, 65536] buffer
+    n, T = 65536, 1024
+    env = ppo_car_b200.VecCarEnv(n, track, device=dev, float_flags=True)
+    env.reset()
+    a = torch.randint(0, 9, (T, n), generator=g, device=dev, dtype=torch.uint8)
+    obs = torch.empty((T, n, 18), device=dev)
+    rew, te, tr = (torch.empty((T, n), device=dev) for _ in range(3))
+    val = torch.randn((T, n), generator=g, device=dev)
+    adv, ret = torch.empty_like(val), torch.empty_like(val)
+    lv, z = torch.randn(n, generator=g, device=dev), torch.zeros(n, device=dev)
+    ms_r = timed(lambda: env.rollout(a, obs_out=obs, reward_out=rew, term_out=te, trunc_out=tr), 3)
+    ms_g = timed(lambda: ppo_car_b200.gae_reverse_scan(rew, val, te, tr, lv, z, z, adv_out=adv, ret_out=ret), 10)
+    out["config3"] = {"workload": "big_track.json, 65,536 envs x 1024 steps: rollout (obs/reward/flags f32 to HBM) + GAE",
+                      "rollout_ms": ms_r, "rollout_env_steps_per_s": n * T / (ms_r * 1e-3), "gae_ms": ms_g,
+                      "gae_gbs": n * T * 24 / (ms_g * 1e-3) / 1e9,
+                      "env_steps_per_s": n * T / ((ms_r + ms_g) * 1e-3)}
+    return out
+
+
+def config5(args):
+    """BASELINE config 5 on 8 GPUs: the PPO loop of ppo_car_b200.train_ppo (README hyper-parameters, 262,144 envs in
+    total, fused rollout + GAE kernel + fused update with the NCCL gradient all-reduce), 4 epochs, the first (lazy
+    initialisation, graph capture) excluded.  Every rank takes part; rank 0 reports."""
+    from ppo_car_b200 import train_ppo
+
+    targs = train_ppo.parse_args(["--track", TRACK, "--n-envs", "262144", "--n-epochs", "4", "--fused-rollout",
+                                  "--fused-update", "--graph-update"])
+    hist = train_ppo.train(targs)
+    per_epoch = [hist[i]["wall_s"] - hist[i - 1]["wall_s"] for i in range(1, len(hist))]
+    ms = 1e3 * sorted(per_epoch)[len(per_epoch) // 2]
+    return {"workload": "PPO loop, README hyper-parameters, 262,144 envs over 8 GPUs x 1024 steps per epoch: fused "
+                        "policy+env rollout, GAE, 80 fused minibatch updates with NCCL gradient all-reduce",
+            "epoch_ms": ms, "env_steps_per_s": 262144 * 1024 / (ms * 1e-3), "epochs_timed": len(per_epoch),
+            "avg_reward_last": hist[-1]["avg_reward"]}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -268,26 +391,48 @@ def run_ours(args):
     value = args.steps * launches * chunk * total / (dev_ms_max * 1e-3)
     slow = env.slow_path_counts()
 
-    # ---- e2e: reference-facing API with HOST buffers (numpy in, numpy out), one env step per call
+    # ---- e2e: reference-facing API with HOST buffers (numpy in, numpy out, the reference's dtypes), one env step per call
     e_steps = args.e2e_steps
     rng = np.random.default_rng(99 + rank)
     host_actions = [rng.integers(0, 9, size=n).astype(np.int64) for _ in range(4)]   # int64: what train.py:185 passes
-    for i in range(2):
-        env.step(host_actions[i % 4])
+    e2e_env = ppo_car_b200.VecCarEnv(n, track, device=dev)    # info = gates_passed / time_passed, as the reference
+    e2e_env.reset()
+    for i in range(3):
+        e2e_env.step(host_actions[i % 4])
     barrier()
     t0 = time.perf_counter()
     sink = 0.0
     for i in range(e_steps):
-        o, r, te, tr, info = env.step(host_actions[i % 4])
+        o, r, te, tr, info = e2e_env.step(host_actions[i % 4])
         sink += float(r[0])                       # the result is on the host (pinned buffer) when step() returns
     barrier()
     t_e2e = time.perf_counter() - t0
+    assert r.dtype == np.float64 and te.dtype == np.bool_ and o.dtype == np.float32
     te2e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
     e2e_value = e_steps * total / float(te2e.item())
-    h2d = total * 1                               # uint8 actions (cast on the host before the copy)
-    d2h = total * (72 + 4 + 1 + 1 + 16)
+    h2d = total * 1                               # uint8 actions (narrowed on the host before the copy)
+    d2h = total * (72 + 16)                       # observation + one 16-byte record (reward, flags, info) per env
+    del e2e_env
+    # the ceiling of that path: pinned device->host copies of one step's results, ALL ranks copying at the same time
+    pb = n * 88
+    d_src = torch.empty(pb, dtype=torch.uint8, device=dev)
+    h_dst = [torch.empty(pb, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    for i in range(2):
+        h_dst[i].copy_(d_src, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    p_reps = 12
+    for i in range(p_reps):
+        h_dst[i % 2].copy_(d_src, non_blocking=True)
+    torch.cuda.synchronize()
+    t_probe = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    barrier()
+    if world > 1:
+        dist.all_reduce(t_probe, op=dist.ReduceOp.MAX)
+    bound_gbs = world * p_reps * pb / float(t_probe.item()) / 1e9
+    del d_src, h_dst
 
     line = None
     if rank == 0:
@@ -342,13 +487,22 @@ def run_ours(args):
         gae_ms = ge[0].elapsed_time(ge[-1]) / 10
         gae_gbs = Tg * Ng * 24 / (gae_ms * 1e-3) / 1e9
         del g_rew, g_val, g_term, g_trunc, g_adv, g_ret
-        traffic = None
-        try:   # measured DRAM bytes per env-step of the same kernel from the committed ncu capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            traffic = tr["dram_bytes_per_env_step"] * steps_per_launch
+        # measured DRAM bytes per env-step of the same kernel from the committed ncu capture — refused (null) when the
+        # capture was taken from other kernel sources than the ones this library was built from
+        traffic, traffic_note = None, "no ncu capture of the current kernel sources under profiles/"
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            if tr.get("source_sha256") == kernel_source_hash():
+                traffic = tr["dram_bytes_per_env_step"] * steps_per_launch
+                traffic_note = (f"DRAM bytes per launch = ncu dram__bytes_read+write per env-step "
+                                f"({tr['dram_bytes_per_env_step']:.2f}, profiles/r2_traffic.json, same kernel sources) x "
+                                "env-steps per launch")
+            else:
+                traffic_note = "profiles/r2_traffic.json was captured from other kernel sources: refused"
         except Exception:
             pass
-        cpu = cpu_baseline(track) if not args.no_cpu else None
+        configs = other_configs(dev, world) if not args.no_configs else None
+        cpu = cpu_baseline() if not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
@@ -363,15 +517,17 @@ def run_ours(args):
             "wall_s": t_wall,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "VecCarEnv.step(numpy int64 actions) -> numpy obs/reward/terminated/truncated/info",
-                    "steps": e_steps},
+                    "api": "VecCarEnv.step(numpy int64 actions) -> numpy obs f32 / reward f64 / terminated, truncated "
+                           "bool / info {gates_passed, time_passed} (the reference's dtypes)",
+                    "steps": e_steps, "bound_gbs": bound_gbs, "achieved_gbs": e2e_value * 88 / 1e9,
+                    "frac_of_bound": e2e_value * 88 / 1e9 / bound_gbs,
+                    "bound_note": f"pinned D2H of {pb / 1e6:.1f} MB per rank x {world} ranks copying concurrently, "
+                                  "measured in this run"},
             "gpu_launches": args.steps * launches,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_nominal, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_nominal, "traffic": traffic,
-                         "traffic_note": "DRAM bytes per launch (ncu dram__bytes_read+write per env-step x env-steps per "
-                                         "launch, profiles/r1_traffic.json); algorithmic bytes per launch = "
-                                         f"{bytes_per_launch}",
-                         "kernel": "k_rollout<uint8,uint8>", "launch_ms": launch_ms,
+                         "traffic_note": traffic_note + f"; algorithmic bytes per launch = {bytes_per_launch}",
+                         "kernel": "k_rollout_tab<uint8,uint8,6>", "launch_ms": launch_ms,
                          "flop_per_env_step": FLOP_PER_ENV_STEP,
                          "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no "
                                         "FP32 entry)",
@@ -383,8 +539,18 @@ def run_ours(args):
                     "peak": hbm_peak, "unit": "GB/s", "frac": gae_gbs / hbm_peak, "bytes_per_element": 24,
                     "note": "inputs + outputs 1.6 GB > L2; 10 back-to-back launches, CUDA events"},
             "slow_path": {k: v for k, v in slow.items()},
+            "configs": configs,
             "cpu_baseline": cpu,
         }
+    if world == 8 and not args.no_configs:                     # BASELINE config 5 needs every rank
+        try:
+            c5 = config5(args)
+        except Exception as exc:                               # reported, not fatal: the headline line stands
+            c5 = {"error": repr(exc)[:300]}
+        if rank == 0 and line is not None:
+            line.setdefault("configs", {})
+            line["configs"] = dict(line["configs"] or {}, config5=c5)
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -401,7 +567,8 @@ def main():
     ap.add_argument("--envs", type=int, default=TOTAL_ENVS, help="total environments over all GPUs")
     ap.add_argument("--chunk", type=int, default=256, help="env steps per rollout launch")
     ap.add_argument("--launches", type=int, default=1, help="rollout launches per timed bench step")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 2 / 3 / 5")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -59,6 +59,8 @@ struct Handle {
     HostTrack host;
     unsigned char *d_blob;    // trig64 | acc64 | gates | trig32 | trig32s | walls64 | segf | segd | den4
     const float4 *d_den4;     // [72][n_pairs] denominators of the pair kernels (null: track without pairs)
+    int host_ranges;          // tuning hook: sub-ranges of the host-buffer step (0 = by size)
+    int4 *cur_rec;            // step records instead of reward / flag arrays for the launch being dispatched (else null)
     int tab;                  // 0 = k_rollout_tab for large launches, 1 = always (where the track allows), -1 = never
     Tables dev;               // device pointers into d_blob
     unsigned long long *d_stats;
@@ -76,17 +78,18 @@ struct Handle {
 // Resources of the host-buffer step path (carenv_step_host): device staging for one step of `cap` environments,
 // a pinned byte buffer the caller's actions are narrowed into, side streams and events for the sub-range pipeline.
 struct HostStep {
-    static constexpr int kMaxRanges = 8;
+    static constexpr int kMaxRanges = 16;
     int cap = 0, flag_bytes = 0;
     unsigned char *d_act = nullptr, *h_act = nullptr;
     float *d_obs = nullptr, *d_rew = nullptr;
     unsigned char *d_term = nullptr, *d_trunc = nullptr;
     int32_t *d_info = nullptr;
+    int4 *d_rec = nullptr;    // carenv_step_host_records: one 16-byte record per environment
     cudaStream_t streams[kMaxRanges] = {};
     cudaEvent_t ready = nullptr, done[kMaxRanges] = {};
     void release() {
         cudaFree(d_act); cudaFreeHost(h_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc);
-        cudaFree(d_info);
+        cudaFree(d_info); cudaFree(d_rec);
         for (int i = 0; i < kMaxRanges; ++i) {
             if (streams[i]) cudaStreamDestroy(streams[i]);
             if (done[i]) cudaEventDestroy(done[i]);
@@ -95,6 +98,19 @@ struct HostStep {
         *this = HostStep();
     }
 };
+
+// float32 rewards of a range of step records -> the float64 array the reference's numpy boundary returns
+// (lib/car_env.py:760: a Python float per env, stacked by the vector env into float64).  float -> double is exact.
+static void widen_rewards(const carenv_step_record *rec, double *out, int m) {
+    int i = 0;
+#if defined(__SSE2__)
+    for (; i + 2 <= m; i += 2) {
+        const __m128 v = _mm_set_ps(0.0f, 0.0f, rec[i + 1].reward, rec[i].reward);
+        _mm_storeu_pd(out + i, _mm_cvtps_pd(v));
+    }
+#endif
+    for (; i < m; ++i) out[i] = (double)rec[i].reward;
+}
 
 // int64 actions (what train.py:185 passes) -> one byte each; anything outside 0..8 acts like 8 (lib/car_env.py:698-722).
 // Runs on the host in front of every sub-range of carenv_step_host, so it is written for SSE2 (4 actions per
@@ -144,6 +160,23 @@ constexpr int kWarpPerEnvMax = 2048;   // n_envs up to which k_rollout_warp is l
 template <typename FlagT> __device__ __forceinline__ FlagT make_flag(int v);
 template <> __device__ __forceinline__ uint8_t make_flag<uint8_t>(int v) { return (uint8_t)v; }
 template <> __device__ __forceinline__ float make_flag<float>(int v) { return v ? 1.0f : 0.0f; }
+
+// Reward / flags / info of one env-step: either the separate arrays of carenv_step / carenv_rollout or ONE 16-byte
+// carenv_step_record (reward f32 | terminated u8 | truncated u8 | pad u16 | gates_passed i32 | time_passed i32) —
+// what the host-buffer step path ships over PCIe.
+template <typename FlagT>
+__device__ __forceinline__ void store_step(const StepResult &o, size_t idx, float *__restrict__ rew_out,
+                                           FlagT *__restrict__ term_out, FlagT *__restrict__ trunc_out,
+                                           int4 *__restrict__ info_out, int4 *__restrict__ rec_out) {
+    if (rec_out) {
+        rec_out[idx] = make_int4(__float_as_int(o.reward), o.terminated | (o.truncated << 8), o.gates_passed, o.time_passed);
+    } else {
+        rew_out[idx] = o.reward;
+        term_out[idx] = make_flag<FlagT>(o.terminated);
+        trunc_out[idx] = make_flag<FlagT>(o.truncated);
+    }
+    if (info_out) info_out[idx] = make_int4(o.gates_passed, o.time_passed, o.next_gate, o.gate_hit | (o.lap << 1));
+}
 
 // Stage the per-thread-indexed tables into shared memory (all sizes are multiples of 8 bytes).
 __device__ __forceinline__ Tables stage_tables(const Tables &G, int n_gates, int n_seg, unsigned char *smem) {
@@ -231,7 +264,8 @@ __global__ void __launch_bounds__(kBlock, CARENV_MIN_BLOCKS)
 k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int n_steps, double2 *__restrict__ pos,
           double2 *__restrict__ vel, int4 *__restrict__ ints, const ActT *__restrict__ actions, double reward_scale,
           float *__restrict__ obs_out, float *__restrict__ rew_out, FlagT *__restrict__ term_out,
-          FlagT *__restrict__ trunc_out, int4 *__restrict__ info_out, unsigned long long *stats, int obs_mode) {
+          FlagT *__restrict__ trunc_out, int4 *__restrict__ info_out, int4 *__restrict__ rec_out,
+          unsigned long long *stats, int obs_mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,10 +292,7 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
         } else if (obs_mode == kObsPose) {                   // 32-byte pose record instead of the 72-byte observation
             store_pose(reinterpret_cast<PoseRec *>(obs_out) + idx, s, o.obs[2], o.obs[3]);
         }
-        rew_out[idx] = o.reward;
-        term_out[idx] = make_flag<FlagT>(o.terminated);
-        trunc_out[idx] = make_flag<FlagT>(o.truncated);
-        if (info_out) info_out[idx] = make_int4(o.gates_passed, o.time_passed, o.next_gate, o.gate_hit | (o.lap << 1));
+        store_step(o, idx, rew_out, term_out, trunc_out, info_out, rec_out);
     }
     pos[e] = make_double2(s.px, s.py);
     vel[e] = make_double2(s.vx, s.vy);
@@ -272,8 +303,8 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
 // like k_rollout, but the 144 denominators cross(e, d) a step needs come from a per-track table in shared memory
 // (TabView, carenv_core.cuh) instead of 144 FMUL2 / FFMA2 — the values are the same bit for bit.  One CTA of up to
 // 512 threads per SM owns the table copies (72 headings x n_pairs x 16 B, x 8 skewed copies = 147 KB on big_track)
-// and walks over blocks of `envs_per_block` environments; the block size is chosen on the host so that every SM
-// gets the same number of blocks (no partial last wave: 131,072 envs are 2 x 148 blocks of 443).
+// and walks over blocks of environments; the block sizes are chosen on the host (launch_rollout_tab) so that every
+// SM gets the same number of blocks and the last round is as short as its remainder allows.
 #ifndef CARENV_TAB_THREADS
 #define CARENV_TAB_THREADS 512
 #endif
@@ -281,11 +312,12 @@ constexpr int kTabThreads = CARENV_TAB_THREADS;
 template <typename ActT, typename FlagT, int U>
 __global__ void __launch_bounds__(kTabThreads, 1)
 k_rollout_tab(const __grid_constant__ TrackParams P, const Tables G, const float4 *__restrict__ den4, int n_pairs,
-              int row_f4, int copies, int table_bytes, int n_envs, int n_steps, int envs_per_block, int n_blocks,
+              int row_f4, int copies, int table_bytes, int n_envs, int n_steps, int epb_main, int n_main, int epb_last,
+              int n_blocks,
               double2 *__restrict__ pos, double2 *__restrict__ vel, int4 *__restrict__ ints,
               const ActT *__restrict__ actions, double reward_scale, float *__restrict__ obs_out,
               float *__restrict__ rew_out, FlagT *__restrict__ term_out, FlagT *__restrict__ trunc_out,
-              int4 *__restrict__ info_out, unsigned long long *stats, int obs_mode) {
+              int4 *__restrict__ info_out, int4 *__restrict__ rec_out, unsigned long long *stats, int obs_mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     // [tables | pad to 128 B | copy 0 | copy 1 (+16 B) | ...]: copy c starts at c * (72 * row + 1) float4
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
@@ -299,11 +331,14 @@ k_rollout_tab(const __grid_constant__ TrackParams P, const Tables G, const float
     }
     const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);      // ends with __syncthreads()
     const TabView tv{tab + (threadIdx.x & (copies - 1)) * copy_f4, row_f4};
-    if ((int)threadIdx.x >= envs_per_block) return;
 
+    // blocks [0, n_main) hold epb_main environments each (full rounds: four warps per scheduler), the blocks of the
+    // last round epb_last (a multiple of 128: every scheduler of the SM gets the same number of warps)
     for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const int e = blk * envs_per_block + threadIdx.x;
-        if (e >= n_envs) break;
+        const bool last = blk >= n_main;
+        if ((int)threadIdx.x >= (last ? epb_last : epb_main)) continue;
+        const int e = last ? n_main * epb_main + (blk - n_main) * epb_last + threadIdx.x : blk * epb_main + threadIdx.x;
+        if (e >= n_envs) continue;
         EnvState s;
         {
             const double2 p = pos[e], v = vel[e];
@@ -325,10 +360,7 @@ k_rollout_tab(const __grid_constant__ TrackParams P, const Tables G, const float
             } else if (obs_mode == kObsPose) {
                 store_pose(reinterpret_cast<PoseRec *>(obs_out) + idx, s, o.obs[2], o.obs[3]);
             }
-            rew_out[idx] = o.reward;
-            term_out[idx] = make_flag<FlagT>(o.terminated);
-            trunc_out[idx] = make_flag<FlagT>(o.truncated);
-            if (info_out) info_out[idx] = make_int4(o.gates_passed, o.time_passed, o.next_gate, o.gate_hit | (o.lap << 1));
+            store_step(o, idx, rew_out, term_out, trunc_out, info_out, rec_out);
         }
         pos[e] = make_double2(s.px, s.py);
         vel[e] = make_double2(s.vx, s.vy);
@@ -347,7 +379,7 @@ k_rollout_warp(const __grid_constant__ TrackParams P, const Tables G, int n_envs
                double2 *__restrict__ vel, int4 *__restrict__ ints, const ActT *__restrict__ actions,
                double reward_scale, float *__restrict__ obs_out, float *__restrict__ rew_out,
                FlagT *__restrict__ term_out, FlagT *__restrict__ trunc_out, int4 *__restrict__ info_out,
-               unsigned long long *stats, int obs_mode) {
+               int4 *__restrict__ rec_out, unsigned long long *stats, int obs_mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);
     const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -381,10 +413,7 @@ k_rollout_warp(const __grid_constant__ TrackParams P, const Tables G, int n_envs
             } else if (obs_mode == kObsPose) {
                 store_pose(reinterpret_cast<PoseRec *>(obs_out) + idx, s, o.obs[2], o.obs[3]);
             }
-            rew_out[idx] = o.reward;
-            term_out[idx] = make_flag<FlagT>(o.terminated);
-            trunc_out[idx] = make_flag<FlagT>(o.truncated);
-            if (info_out) info_out[idx] = make_int4(o.gates_passed, o.time_passed, o.next_gate, o.gate_hit | (o.lap << 1));
+            store_step(o, idx, rew_out, term_out, trunc_out, info_out, rec_out);
         }
     }
     if (lane == 0) {
@@ -936,7 +965,7 @@ int launch_rollout_t(Handle *h, int n_envs, int n_steps, double *pos, double *ve
         h->host.P, h->dev, n_envs, n_steps, reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel),
         reinterpret_cast<int4 *>(ints), static_cast<const ActT *>(actions), reward_scale, obs_out, reward_out,
         static_cast<FlagT *>(term_out), static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out),
-        h->d_stats, obs_mode);
+        h->cur_rec, h->d_stats, obs_mode);
     CU(cudaGetLastError());
     return 0;
 }
@@ -956,21 +985,26 @@ int launch_rollout_tab(Handle *h, int U, int n_envs, int n_steps, double *pos, d
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int block = h->block > 0 ? h->block * 4 : kTabThreads;           // tuning hook (block is 0..128: x4)
-    const long long per_wave = (long long)sms * block;
-    const int rounds = (int)((n_envs + per_wave - 1) / per_wave);
-    int epb = (int)((n_envs + (long long)sms * rounds - 1) / ((long long)sms * rounds));
-    epb = (epb + 31) / 32 * 32;
-    if (epb > block) epb = block;
-    const int n_blocks = (n_envs + epb - 1) / epb;
+    // A round = one block per SM.  Its duration is set by the warps per SCHEDULER (a block of 448 environments takes as
+    // long as one of 512), so all rounds but the last are full blocks and the last round's blocks are the smallest
+    // multiple of 128 environments that covers the remainder: 131,072 envs on 148 SMs = 148 x 512 + 148 x 384.
+    const long long per_round = (long long)sms * block;
+    const int rounds = (int)((n_envs + per_round - 1) / per_round);
+    const int n_main = (rounds - 1) * sms, epb_main = block;
+    const int rem = n_envs - n_main * epb_main;
+    int epb_last = ((rem + sms - 1) / sms + 127) / 128 * 128;
+    if (epb_last > block) epb_last = block;
+    const int n_blocks = n_main + (rem + epb_last - 1) / epb_last;
     const int grid = n_blocks < sms ? n_blocks : sms;
     const size_t smem = total(copies);
     auto launch = [&](auto kern) -> int {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, block, smem, stream>>>(
-            h->host.P, h->dev, h->d_den4, n_pairs, row_f4, copies, table_bytes, n_envs, n_steps, epb, n_blocks,
+            h->host.P, h->dev, h->d_den4, n_pairs, row_f4, copies, table_bytes, n_envs, n_steps, epb_main, n_main, epb_last,
+            n_blocks,
             reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints),
             static_cast<const ActT *>(actions), reward_scale, obs_out, reward_out, static_cast<FlagT *>(term_out),
-            static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out), h->d_stats, obs_mode);
+            static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out), h->cur_rec, h->d_stats, obs_mode);
         CU(cudaGetLastError());
         return 0;
     };
@@ -988,12 +1022,14 @@ int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel,
     const bool warp_ok = h->host.P.n_seg <= 32 && !h->force_generic;
     if (warp_ok && (h->warp_per_env == 1 || (h->warp_per_env == 0 && n_envs <= kWarpPerEnvMax))) {
         auto kern = k_rollout_warp<ActT, FlagT>;
+        if (h->smem_bytes > 48 * 1024)                       // tracks with more than ~900 gates
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
         const int grid = (n_envs + 3) / 4;
         kern<<<grid, 128, h->smem_bytes, stream>>>(
             h->host.P, h->dev, n_envs, n_steps, reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel),
             reinterpret_cast<int4 *>(ints), static_cast<const ActT *>(actions), reward_scale, obs_out, reward_out,
             static_cast<FlagT *>(term_out), static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out),
-            h->d_stats, obs_mode);
+            h->cur_rec, h->d_stats, obs_mode);
         CU(cudaGetLastError());
         return 0;
     }
@@ -1003,7 +1039,7 @@ int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel,
     // large launches: denominators from the shared-memory table (k_rollout_tab).  "Large" = at least two warps per
     // scheduler on every SM and enough steps to amortise staging the table copies (147 KB per CTA on big_track).
     if (U >= 2 && h->d_den4 && h->tab >= 0 &&
-        (h->tab == 1 || (n_envs >= 148 * 256 && (long long)n_envs * n_steps >= (1LL << 22)))) {
+        (h->tab == 1 || (n_envs >= 148 * 384 && (long long)n_envs * n_steps >= (1LL << 22)))) {
         const int rc = launch_rollout_tab<ActT, FlagT>(h, U, n_envs, n_steps, pos, vel, ints, actions, reward_scale,
                                                        obs_out, reward_out, term_out, trunc_out, info_out, stream,
                                                        obs_mode);
@@ -1027,7 +1063,7 @@ int dispatch_rollout(void *handle, int n_envs, int n_steps, double *pos, double 
     if (n_envs < 0 || n_steps < 0) return fail(CARENV_E_INVAL, "negative n_envs / n_steps");
     if (n_envs == 0 || n_steps == 0) return 0;
     if (!obs_out) obs_mode = kObsNone;
-    if (!pos || !vel || !ints || !actions || !reward_out || !term_out || !trunc_out)
+    if (!pos || !vel || !ints || !actions || (!h->cur_rec && (!reward_out || !term_out || !trunc_out)))
         return fail(CARENV_E_INVAL, "null state / action / output pointer");
     DeviceGuard guard(h->device);
     if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
@@ -1067,7 +1103,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0; h->warp_per_env = 0; h->hs = nullptr; h->d_den4 = nullptr; h->tab = 0;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0; h->warp_per_env = 0; h->hs = nullptr; h->d_den4 = nullptr; h->tab = 0; h->cur_rec = nullptr; h->host_ranges = 0;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -1188,14 +1224,18 @@ int carenv_host_free(void *ptr) {
     return 0;
 }
 
-int carenv_step_host(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions_host,
-                     int action_dtype, double reward_scale, float *obs_host, float *reward_host, void *term_host,
-                     void *trunc_host, int flag_dtype, int32_t *info_host, void *stream) {
+// Shared implementation of the host-buffer steps.  `rec_host` != null: record mode (one 16-byte record per environment
+// instead of the reward / flag arrays; optionally `reward64_host`, widened on this thread range by range while the
+// later ranges are still in flight).
+static int step_host_impl(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions_host,
+                          int action_dtype, double reward_scale, float *obs_host, float *reward_host, void *term_host,
+                          void *trunc_host, int flag_dtype, int32_t *info_host, carenv_step_record *rec_host,
+                          double *reward64_host, void *stream) {
     Handle *h = static_cast<Handle *>(handle);
     if (!h) return fail(CARENV_E_INVAL, "null handle");
     if (n_envs < 0) return fail(CARENV_E_INVAL, "negative n_envs");
     if (n_envs == 0) return 0;
-    if (!pos || !vel || !ints || !actions_host || !obs_host || !reward_host || !term_host || !trunc_host)
+    if (!pos || !vel || !ints || !actions_host || !obs_host || (!rec_host && (!reward_host || !term_host || !trunc_host)))
         return fail(CARENV_E_INVAL, "null state / action / output pointer");
     if (action_dtype != CARENV_ACT_U8 && action_dtype != CARENV_ACT_I32 && action_dtype != CARENV_ACT_I64)
         return fail(CARENV_E_INVAL, "unknown action_dtype");
@@ -1215,6 +1255,7 @@ int carenv_step_host(void *handle, int n_envs, double *pos, double *vel, int32_t
         if (e == cudaSuccess) e = cudaMalloc(&S.d_term, n * fb);
         if (e == cudaSuccess) e = cudaMalloc(&S.d_trunc, n * fb);
         if (e == cudaSuccess) e = cudaMalloc(&S.d_info, n * 4 * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&S.d_rec, n * sizeof(int4));
         for (int i = 0; i < HostStep::kMaxRanges && e == cudaSuccess; ++i) {
             e = cudaStreamCreateWithFlags(&S.streams[i], cudaStreamNonBlocking);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.done[i], cudaEventDisableTiming);
@@ -1223,15 +1264,19 @@ int carenv_step_host(void *handle, int n_envs, double *pos, double *vel, int32_t
         if (e != cudaSuccess) { S.release(); return cuda_fail(e, "carenv_step_host: staging allocation"); }
         S.cap = n_envs; S.flag_bytes = fb;
     }
-    // sub-ranges of about 65,536 environments (6 MB of results): the cast + H2D + kernel of range i + 1 overlap the
-    // D2H copy of range i, which is the bottleneck (94 B per environment over PCIe)
-    int n_ranges = n_envs / 65536;
+    // Sub-ranges sized by bytes (16,384 environments = 1.4 MB of results, at most 16 ranges): the narrowing + H2D +
+    // kernel of range i + 1 overlap the D2H copies of range i, which are the bottleneck (88 B per environment over
+    // PCIe in record mode).  A 131,072-environment shard of an 8-GPU job gets an 8-deep pipeline, not a 2-deep one.
+    int n_ranges = n_envs / 16384;
     n_ranges = n_ranges < 1 ? 1 : (n_ranges > HostStep::kMaxRanges ? HostStep::kMaxRanges : n_ranges);
+    if (h->host_ranges > 0) n_ranges = h->host_ranges > HostStep::kMaxRanges ? HostStep::kMaxRanges : h->host_ranges;
+    if (n_ranges > n_envs) n_ranges = n_envs;
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     CU(cudaEventRecord(S.ready, user));                       // earlier work on the caller's stream (reset, device steps)
+    int lo_of[HostStep::kMaxRanges + 1];
+    for (int r = 0; r <= n_ranges; ++r) lo_of[r] = (int)((long long)n_envs * r / n_ranges);
     for (int r = 0; r < n_ranges; ++r) {
-        const int lo = (int)((long long)n_envs * r / n_ranges), hi = (int)((long long)n_envs * (r + 1) / n_ranges);
-        const int m = hi - lo;
+        const int lo = lo_of[r], m = lo_of[r + 1] - lo;
         if (action_dtype == CARENV_ACT_I64) {
             narrow_actions_i64(static_cast<const unsigned long long *>(actions_host) + lo, S.h_act + lo, m);
         } else if (action_dtype == CARENV_ACT_I32) {
@@ -1244,26 +1289,64 @@ int carenv_step_host(void *handle, int n_envs, double *pos, double *vel, int32_t
         cudaStream_t st = S.streams[r];
         CU(cudaStreamWaitEvent(st, S.ready, 0));
         CU(cudaMemcpyAsync(S.d_act + lo, S.h_act + lo, (size_t)m, cudaMemcpyHostToDevice, st));
+        h->cur_rec = rec_host ? reinterpret_cast<int4 *>(S.d_rec) + lo : nullptr;
         const int rc = dispatch_rollout(h, m, 1, pos + 2 * (size_t)lo, vel + 2 * (size_t)lo, ints + 4 * (size_t)lo,
                                         S.d_act + lo, CARENV_ACT_U8, reward_scale, S.d_obs + (size_t)lo * kObsDim,
                                         S.d_rew + lo, S.d_term + (size_t)lo * fb, S.d_trunc + (size_t)lo * fb, flag_dtype,
                                         info_host ? S.d_info + 4 * (size_t)lo : nullptr, st, kObsFull);
+        h->cur_rec = nullptr;
         if (rc != 0) return rc;
         CU(cudaMemcpyAsync(obs_host + (size_t)lo * kObsDim, S.d_obs + (size_t)lo * kObsDim,
                            (size_t)m * kObsDim * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(reward_host + lo, S.d_rew + lo, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(static_cast<unsigned char *>(term_host) + (size_t)lo * fb, S.d_term + (size_t)lo * fb,
-                           (size_t)m * fb, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(static_cast<unsigned char *>(trunc_host) + (size_t)lo * fb, S.d_trunc + (size_t)lo * fb,
-                           (size_t)m * fb, cudaMemcpyDeviceToHost, st));
+        if (rec_host) {
+            CU(cudaMemcpyAsync(rec_host + lo, S.d_rec + lo, (size_t)m * sizeof(int4), cudaMemcpyDeviceToHost, st));
+        } else {
+            CU(cudaMemcpyAsync(reward_host + lo, S.d_rew + lo, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(static_cast<unsigned char *>(term_host) + (size_t)lo * fb, S.d_term + (size_t)lo * fb,
+                               (size_t)m * fb, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(static_cast<unsigned char *>(trunc_host) + (size_t)lo * fb, S.d_trunc + (size_t)lo * fb,
+                               (size_t)m * fb, cudaMemcpyDeviceToHost, st));
+        }
         if (info_host)
             CU(cudaMemcpyAsync(info_host + 4 * (size_t)lo, S.d_info + 4 * (size_t)lo, (size_t)m * 4 * sizeof(int32_t),
                                cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(S.done[r], st));
     }
     for (int r = 0; r < n_ranges; ++r) CU(cudaStreamWaitEvent(user, S.done[r], 0));   // later device work sees the new state
-    for (int r = 0; r < n_ranges; ++r) CU(cudaEventSynchronize(S.done[r]));           // results are in the host buffers
+    for (int r = 0; r < n_ranges; ++r) {                                              // results are in the host buffers
+        CU(cudaEventSynchronize(S.done[r]));
+        if (rec_host && reward64_host) widen_rewards(rec_host + lo_of[r], reward64_host + lo_of[r], lo_of[r + 1] - lo_of[r]);
+    }
     return 0;
+}
+
+int carenv_step_host(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions_host,
+                     int action_dtype, double reward_scale, float *obs_host, float *reward_host, void *term_host,
+                     void *trunc_host, int flag_dtype, int32_t *info_host, void *stream) {
+    return step_host_impl(handle, n_envs, pos, vel, ints, actions_host, action_dtype, reward_scale, obs_host, reward_host,
+                          term_host, trunc_host, flag_dtype, info_host, nullptr, nullptr, stream);
+}
+
+int carenv_step_host_records(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions_host,
+                             int action_dtype, double reward_scale, float *obs_host, carenv_step_record *rec_host,
+                             double *reward64_host, int32_t *debug_info_host, void *stream) {
+    if (!rec_host) return fail(CARENV_E_INVAL, "carenv_step_host_records needs rec_host");
+    static_assert(sizeof(carenv_step_record) == 16, "record layout");
+    return step_host_impl(handle, n_envs, pos, vel, ints, actions_host, action_dtype, reward_scale, obs_host, nullptr,
+                          nullptr, nullptr, CARENV_FLAG_U8, debug_info_host, rec_host, reward64_host, stream);
+}
+
+int carenv_step_records(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions,
+                        int action_dtype, double reward_scale, float *obs_out, carenv_step_record *rec_out,
+                        int32_t *debug_info_out, void *stream) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(CARENV_E_INVAL, "null handle");
+    if (!obs_out || !rec_out) return fail(CARENV_E_INVAL, "carenv_step_records needs obs_out and rec_out");
+    h->cur_rec = reinterpret_cast<int4 *>(rec_out);
+    const int rc = dispatch_rollout(handle, n_envs, 1, pos, vel, ints, actions, action_dtype, reward_scale, obs_out, nullptr,
+                                    nullptr, nullptr, CARENV_FLAG_U8, debug_info_out, stream, kObsFull);
+    h->cur_rec = nullptr;
+    return rc;
 }
 
 int carenv_observe(void *handle, long long n, const void *poses, const long long *index, float *obs_out,
@@ -1463,6 +1546,7 @@ int carenv_set_option(void *handle, const char *name, int value) {
         h->block = value; return 0;
     }
     if (std::string(name) == "pose_rows") { h->pose_rows = value ? 1 : 0; return 0; }
+    if (std::string(name) == "host_ranges") { h->host_ranges = value < 0 ? 0 : value; return 0; }
     if (std::string(name) == "tab") { h->tab = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
     if (std::string(name) == "warp_per_env") { h->warp_per_env = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
     if (std::string(name) == "tc_tiles") {

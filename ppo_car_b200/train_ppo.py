@@ -69,6 +69,10 @@ class ActorCritic(nn.Module):
 def parse_args(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument("--run-name", default="b200")
+    p.add_argument("--checkpoint-dir", default=None,
+                   help="directory for checkpoint_{epoch}.dat (every 10 epochs) and model.dat (at exit), the "
+                        "reference's files (train.py:280-283, 301); a sub-directory named after --run-name is created. "
+                        "Default: no checkpoints")
     p.add_argument("--track", default="big_track", help="track name shipped with the package or a JSON path")
     p.add_argument("--n-envs", type=int, default=16, help="total environments over all ranks")
     p.add_argument("--n-epochs", type=int, default=200)
@@ -149,7 +153,16 @@ def train(args) -> list[dict]:
     next_term = torch.zeros(n, device=dev)
     next_trunc = torch.zeros(n, device=dev)
     history, global_step, t_start = [], 0, time.time()
-    n_mb = max(1, T // args.batch_size)
+    n_mb = -(-T // args.batch_size)                        # range(0, n_steps, batch_size): ceil (train.py:228)
+    ckpt_dir = None
+    if args.checkpoint_dir and rank == 0:                  # train.py:125-126: checkpoints/<run>/
+        ckpt_dir = os.path.join(args.checkpoint_dir, args.run_name)
+        os.makedirs(ckpt_dir, exist_ok=True)
+
+    def save_checkpoint(name):
+        """The keys are the reference Agent's (actor.0.weight ... critic.2.bias): loads into lib/model.py:Agent."""
+        if ckpt_dir is not None:
+            torch.save({k: v.detach().cpu() for k, v in agent.state_dict().items()}, os.path.join(ckpt_dir, name))
 
     def rollout():
         """train.py:173-195 with everything on the device: row t of the buffer gets (obs_t, a_t, r_t, V(obs_t),
@@ -190,109 +203,114 @@ def train(args) -> list[dict]:
             with torch.cuda.graph(graph):
                 rollout()
 
-    for epoch in range(1, args.n_epochs + 1):
-        # ---- rollout
-        with torch.no_grad():
-            if packed is not None:
-                pack_policy(agent.actor, agent.critic, out=packed)
-                fused_rollout(envs, packed, buf, next_obs, next_term, next_trunc, seed=args.seed,
-                              step0=(epoch - 1) * T, env_offset=lo, last_val=last_val)
-                boot = last_val.reshape(1, -1)
-            else:
-                if graph is not None:
-                    graph.replay()
-                    buf.ptr = T
+    try:
+        for epoch in range(1, args.n_epochs + 1):
+            # ---- rollout
+            with torch.no_grad():
+                if packed is not None:
+                    pack_policy(agent.actor, agent.critic, out=packed)
+                    fused_rollout(envs, packed, buf, next_obs, next_term, next_trunc, seed=args.seed,
+                                  step0=(epoch - 1) * T, env_offset=lo, last_val=last_val)
+                    boot = last_val.reshape(1, -1)
                 else:
-                    rollout()
-                boot = agent.value(next_obs).reshape(1, -1)
-            global_step += T * args.n_envs
-            adv, ret = buf.calculate_advantages(boot, next_term.reshape(1, -1), next_trunc.reshape(1, -1))
-        rew_sum, steps, episodes = allreduce_rollout_stats(buf.rew_buf.sum(), torch.tensor(float(T * n), device=dev),
-                                                           buf.term_buf.sum() + buf.trunc_buf.sum())
-        obs_b, act_b, val_b, logp_b = buf.get()
-        obs_f = obs_b if args.compact_obs else obs_b.view(-1, *obs_dim)      # pose records / observations
-        act_f, logp_f = act_b.view(-1), logp_b.view(-1)
-        adv_f, ret_f = adv.view(-1), ret.view(-1)
+                    if graph is not None:
+                        graph.replay()
+                        buf.ptr = T
+                    else:
+                        rollout()
+                    boot = agent.value(next_obs).reshape(1, -1)
+                global_step += T * args.n_envs
+                adv, ret = buf.calculate_advantages(boot, next_term.reshape(1, -1), next_trunc.reshape(1, -1))
+            rew_sum, steps, episodes = allreduce_rollout_stats(buf.rew_buf.sum(), torch.tensor(float(T * n), device=dev),
+                                                               buf.term_buf.sum() + buf.trunc_buf.sum())
+            obs_b, act_b, val_b, logp_b = buf.get()
+            obs_f = obs_b if args.compact_obs else obs_b.view(-1, *obs_dim)      # pose records / observations
+            act_f, logp_f = act_b.view(-1), logp_b.view(-1)
+            adv_f, ret_f = adv.view(-1), ret.view(-1)
 
-        # ---- update (train.py:223-261)
-        if epoch == 1:
-            sums = torch.zeros(4, device=dev)
-            idx_static = torch.zeros(args.batch_size, dtype=torch.int64, device=dev)
+            # ---- update (train.py:223-261)
+            if epoch == 1:
+                sums = torch.zeros(4, device=dev)
+                idx_static = torch.zeros(args.batch_size, dtype=torch.int64, device=dev)
 
-            def update_step():
-                """One minibatch: draw indices, clipped-surrogate loss, backward, (all-reduce), clip, Adam."""
-                torch.randint(0, T * n, (args.batch_size,), device=dev, out=idx_static)
-                idx = idx_static
-                if fused_upd is not None:
-                    obs_in = envs.observe(obs_f, idx) if args.compact_obs else obs_f
-                    fused_upd.grad(obs_in, idx, act_f, logp_f, adv_f, ret_f, obs_is_gathered=args.compact_obs)
-                    fused_upd.apply(world)
-                    return
-                obs_mb = envs.observe(obs_f, idx) if args.compact_obs else obs_f[idx]
-                _, new_logp, ent, new_val = agent.act(obs_mb, act_f[idx])
-                ratio = torch.exp(new_logp - logp_f[idx])
-                a = adv_f[idx]
-                a = (a - a.mean()) / torch.clamp(a.std(), min=1e-5)
-                pol = torch.max(-a * ratio, -a * torch.clamp(ratio, 1 - args.clip_ratio, 1 + args.clip_ratio)).mean()
-                vl = 0.5 * ((new_val.view(-1) - ret_f[idx]) ** 2).mean()
-                e = ent.mean()
-                loss = pol + args.vf_coef * vl - args.ent_coef * e
-                opt.zero_grad(set_to_none=True)
-                loss.backward()
-                if world > 1:                                   # average the 12,298 gradients over the shards
-                    flat = torch.cat([p.grad.reshape(-1) for p in params])
-                    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-                    flat /= world
-                    off = 0
-                    for p in params:
-                        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                        off += p.numel()
-                nn.utils.clip_grad_norm_(params, args.max_grad_norm)
-                opt.step()
-                sums.add_(torch.stack([pol.detach(), vl.detach(), e.detach(), loss.detach()]))
+                def update_step():
+                    """One minibatch: draw indices, clipped-surrogate loss, backward, (all-reduce), clip, Adam."""
+                    torch.randint(0, T * n, (args.batch_size,), device=dev, out=idx_static)
+                    idx = idx_static
+                    if fused_upd is not None:
+                        obs_in = envs.observe(obs_f, idx) if args.compact_obs else obs_f
+                        fused_upd.grad(obs_in, idx, act_f, logp_f, adv_f, ret_f, obs_is_gathered=args.compact_obs)
+                        fused_upd.apply(world)
+                        return
+                    obs_mb = envs.observe(obs_f, idx) if args.compact_obs else obs_f[idx]
+                    _, new_logp, ent, new_val = agent.act(obs_mb, act_f[idx])
+                    ratio = torch.exp(new_logp - logp_f[idx])
+                    a = adv_f[idx]
+                    a = (a - a.mean()) / torch.clamp(a.std(), min=1e-5)
+                    pol = torch.max(-a * ratio, -a * torch.clamp(ratio, 1 - args.clip_ratio, 1 + args.clip_ratio)).mean()
+                    vl = 0.5 * ((new_val.view(-1) - ret_f[idx]) ** 2).mean()
+                    e = ent.mean()
+                    loss = pol + args.vf_coef * vl - args.ent_coef * e
+                    opt.zero_grad(set_to_none=True)
+                    loss.backward()
+                    if world > 1:                                   # average the 12,298 gradients over the shards
+                        flat = torch.cat([p.grad.reshape(-1) for p in params])
+                        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                        flat /= world
+                        off = 0
+                        for p in params:
+                            p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                            off += p.numel()
+                    nn.utils.clip_grad_norm_(params, args.max_grad_norm)
+                    opt.step()
+                    sums.add_(torch.stack([pol.detach(), vl.detach(), e.detach(), loss.detach()]))
 
-            update_graph = None
-            if graph_update:                                # obs_f, act_f, ... are views of the static buffer tensors
-                side = torch.cuda.Stream(device=dev)
-                side.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(side):
-                    for _ in range(3):                      # warm-up (also creates Adam's state) counts as 3 real steps
+                update_graph = None
+                if graph_update:                                # obs_f, act_f, ... are views of the static buffer tensors
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        for _ in range(3):                      # warm-up (also creates Adam's state) counts as 3 real steps
+                            update_step()
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    update_graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(update_graph):
                         update_step()
-                torch.cuda.current_stream(dev).wait_stream(side)
-                update_graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(update_graph):
+                    sums.zero_()
+            sums.zero_()
+            if fused_upd is not None:
+                fused_upd.sums.zero_()
+            for _ in range(args.train_iters * n_mb):
+                if update_graph is not None:
+                    update_graph.replay()
+                else:
                     update_step()
-                sums.zero_()
-        sums.zero_()
-        if fused_upd is not None:
-            fused_upd.sums.zero_()
-        for _ in range(args.train_iters * n_mb):
-            if update_graph is not None:
-                update_graph.replay()
+            if fused_upd is not None:
+                fused_upd.lr.mul_(args.learning_rate_decay)
+                sums.copy_(fused_upd.sums)
+            elif sched is not None:
+                sched.step()
             else:
-                update_step()
-        if fused_upd is not None:
-            fused_upd.lr.mul_(args.learning_rate_decay)
-            sums.copy_(fused_upd.sums)
-        elif sched is not None:
-            sched.step()
-        else:
-            opt.param_groups[0]["lr"].mul_(args.learning_rate_decay)
+                opt.param_groups[0]["lr"].mul_(args.learning_rate_decay)
 
-        s = (sums / args.train_iters).tolist()
-        rec = {"epoch": epoch, "global_step": global_step, "avg_reward": rew_sum / steps / args.reward_scaling,
-               "episodes": episodes, "policy_loss": s[0], "value_loss": s[1], "entropy": s[2], "total_loss": s[3],
-               "lr": float(fused_upd.lr if fused_upd is not None else opt.param_groups[0]["lr"]), "sps": global_step / (time.time() - t_start),
-               "wall_s": time.time() - t_start}
-        history.append(rec)
-        if rank == 0:
-            print(f"Epoch {epoch} done in {rec['wall_s']:.2f}s. Avg reward: {rec['avg_reward']:.4f}. "
-                  f"SPS {rec['sps']:.0f}  entropy {rec['entropy']:.3f}", flush=True)
-            if args.log_json:
-                import json
+            s = (sums / args.train_iters).tolist()
+            rec = {"epoch": epoch, "global_step": global_step, "avg_reward": rew_sum / steps / args.reward_scaling,
+                   "episodes": episodes, "policy_loss": s[0], "value_loss": s[1], "entropy": s[2], "total_loss": s[3],
+                   "lr": float(fused_upd.lr if fused_upd is not None else opt.param_groups[0]["lr"]), "sps": global_step / (time.time() - t_start),
+                   "wall_s": time.time() - t_start}
+            history.append(rec)
+            if rank == 0:
+                print(f"Epoch {epoch} done in {rec['wall_s']:.2f}s. Avg reward: {rec['avg_reward']:.4f}. "
+                      f"SPS {rec['sps']:.0f}  entropy {rec['entropy']:.3f}", flush=True)
+                if args.log_json:
+                    import json
 
-                with open(args.log_json, "a") as fh:
-                    fh.write(json.dumps(rec) + "\n")
+                    with open(args.log_json, "a") as fh:
+                        fh.write(json.dumps(rec) + "\n")
+            if epoch % 10 == 0:
+                save_checkpoint(f"checkpoint_{epoch}.dat")
+    finally:                                               # train.py:294-301
+        save_checkpoint("model.dat")
     envs.close()
     return history
 

@@ -11,10 +11,16 @@ sm_100a kernels of libcarenv_b200.so.  There is no CPU path: constructing a VecC
 without the built library or without a CUDA device raises.
 
 Two calling conventions for ``step``:
-  * CUDA tensor in  -> CUDA tensors out (no host round trip; int64/int32/uint8 actions).
-  * numpy array in  -> numpy arrays out (the reference's convention, train.py:185): actions are
-    staged through pinned host memory, results are copied back into pinned buffers and
-    returned as numpy views that stay valid until the next call.
+  * CUDA tensor in  -> CUDA tensors out (no host round trip; int64/int32/uint8 actions; float32 rewards).
+  * numpy array in  -> numpy arrays out (the reference's convention, train.py:185) with the reference's dtypes:
+    float32 observations, FLOAT64 rewards, bool flags, int info.  Actions are staged through pinned host memory,
+    results come back as an observation array plus one 16-byte record per environment (carenv_step_host_records);
+    flags and info are strided numpy views of the record array.
+
+BUFFER LIFETIME (differs from the reference, which returns fresh arrays): everything ``reset`` / ``step`` return
+is a view of buffers owned by this object and is OVERWRITTEN BY THE NEXT ``step`` / ``reset``.  Code that keeps a
+result across a step (``train.py:176-195`` stores the previous ``next_obs`` / ``next_terminateds`` after calling
+``envs.step``) must ``.clone()`` / ``.copy()`` it first, or construct the env with ``copy_outputs=True``.
 """
 from __future__ import annotations
 
@@ -55,7 +61,11 @@ def _ptr(t):
 
 class VecCarEnv:
     def __init__(self, n_envs: int, track_path: str | None = None, device="cuda", reward_scaling: float = 1.0,
-                 float_flags: bool = False, with_info: bool = True, _out: dict | None = None):
+                 float_flags: bool = False, with_info: bool = True, _out: dict | None = None,
+                 copy_outputs: bool = False, debug_info: bool = False):
+        """``copy_outputs=True``: step / reset return fresh copies (the reference's semantics) instead of views of the
+        internal buffers.  ``debug_info=True``: the numpy step also returns ``next_gate_index`` and ``events`` (16 more
+        bytes per environment over PCIe; the parity tests use them)."""
         if n_envs < 1:
             raise ValueError("n_envs must be >= 1")
         self._L = _lib.lib()                       # raises if the CUDA extension is missing
@@ -70,6 +80,8 @@ class VecCarEnv:
         self.reward_scaling = float(reward_scaling)
         self.float_flags = bool(float_flags)
         self.with_info = bool(with_info)
+        self.copy_outputs = bool(copy_outputs)
+        self.debug_info = bool(debug_info)
         low = np.array([0, 0, -1, -1, -1, -1] + [0] * 12, np.float32)
         high = np.ones(OBS_DIM, np.float32)
         self.single_observation_space = Box(low, high)
@@ -132,7 +144,8 @@ class VecCarEnv:
         _lib.check(rc, "carenv_reset")
         self._needs_reset = False
         zeros = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
-        return self._obs, {"gates_passed": zeros, "time_passed": zeros.clone()}
+        obs = self._obs.clone() if self.copy_outputs else self._obs
+        return obs, {"gates_passed": zeros, "time_passed": zeros.clone()}
 
     def _info_dict(self, info):
         if info is None:
@@ -143,7 +156,10 @@ class VecCarEnv:
 
     def step(self, actions):
         """One step of every environment with same-step autoreset (lib/car_env.py:693-760 +
-        gymnasium AsyncVectorEnv).  Returns (obs, rewards, terminateds, truncateds, info)."""
+        gymnasium AsyncVectorEnv).  Returns (obs, rewards, terminateds, truncateds, info).
+
+        The returned tensors / arrays are views of internal buffers that the NEXT step() overwrites (see the
+        module docstring); clone / copy what must survive a step, or use ``copy_outputs=True``."""
         if self._needs_reset:
             raise _lib.CarEnvError("call reset() before step()")
         if isinstance(actions, torch.Tensor) and actions.is_cuda:
@@ -167,20 +183,28 @@ class VecCarEnv:
         _lib.check(rc, "carenv_step")
         term = self._term if self.float_flags else self._term.view(torch.bool)
         trunc = self._trunc if self.float_flags else self._trunc.view(torch.bool)
+        if self.copy_outputs:
+            info = None if self._info is None else self._info.clone()
+            return self._obs.clone(), self._rew.clone(), term.clone(), trunc.clone(), self._info_dict(info)
         return self._obs, self._rew, term, trunc, self._info_dict(self._info)
 
+    _REC_DTYPE = np.dtype([("reward", "<f4"), ("terminated", "?"), ("truncated", "?"), ("pad", "<u2"),
+                           ("gates_passed", "<i4"), ("time_passed", "<i4")])      # carenv_step_record, 16 bytes
+
     def _step_host(self, actions: np.ndarray):
-        """numpy in -> numpy out through carenv_step_host: the library narrows the actions into a pinned buffer and
-        pipelines H2D copy, kernel and D2H copies over sub-ranges of the batch (the D2H copy of the observations is
-        the bottleneck: 94 B per env over PCIe); the results land in pinned host tensors owned by this object."""
+        """numpy in -> numpy out through carenv_step_host_records: the library narrows the actions into a pinned
+        buffer and pipelines H2D copy, kernel and D2H copies over sub-ranges of the batch (the D2H copy is the
+        bottleneck: 88 B per env over PCIe — the observation and one 16-byte record); rewards are widened to the
+        reference's float64 on the host while later ranges are still in flight.  Flags and info are strided views
+        of the pinned record array (float_flags=True returns float32 copies instead)."""
         n = self.num_envs
         if actions.size != n:
             raise ValueError(f"expected {n} actions, got {actions.size}")
         if self._host is None:
             pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
-            self._host = dict(obs=pin((n, OBS_DIM), torch.float32), rew=pin((n,), torch.float32),
-                              term=pin((n,), self._term.dtype), trunc=pin((n,), self._trunc.dtype),
-                              info=pin((n, 4), torch.int32) if self.with_info else None)
+            self._host = dict(obs=pin((n, OBS_DIM), torch.float32), rec=pin((n, 16), torch.uint8),
+                              rew64=pin((n,), torch.float64),
+                              dbg=pin((n, 4), torch.int32) if self.debug_info else None)
         h = self._host
         flat = np.ascontiguousarray(actions.reshape(-1))
         if flat.dtype == np.uint8:
@@ -191,15 +215,25 @@ class VecCarEnv:
             flat = flat.astype(np.int64, copy=False)
             code = _lib.ACT_I64
         with torch.cuda.device(self.device):
-            rc = self._L.carenv_step_host(self._handle, n, _ptr(self.pos), _ptr(self.vel), _ptr(self.ints),
-                                          C.c_void_p(flat.ctypes.data), code, self.reward_scaling, _ptr(h["obs"]),
-                                          _ptr(h["rew"]), _ptr(h["term"]), _ptr(h["trunc"]),
-                                          _lib.FLAG_F32 if self.float_flags else _lib.FLAG_U8,
-                                          _ptr(h["info"]) if self.with_info else None, self._stream())
-        _lib.check(rc, "carenv_step_host")
-        flags = (lambda t: t.numpy()) if self.float_flags else (lambda t: t.numpy().view(np.bool_))
-        info = self._info_dict(h["info"].numpy()) if self.with_info else {}
-        return h["obs"].numpy(), h["rew"].numpy(), flags(h["term"]), flags(h["trunc"]), info
+            rc = self._L.carenv_step_host_records(self._handle, n, _ptr(self.pos), _ptr(self.vel), _ptr(self.ints),
+                                                  C.c_void_p(flat.ctypes.data), code, self.reward_scaling,
+                                                  _ptr(h["obs"]), _ptr(h["rec"]), _ptr(h["rew64"]), _ptr(h["dbg"]),
+                                                  self._stream())
+        _lib.check(rc, "carenv_step_host_records")
+        rec = h["rec"].numpy().view(self._REC_DTYPE).reshape(n)
+        obs, rew, term, trunc = h["obs"].numpy(), h["rew64"].numpy(), rec["terminated"], rec["truncated"]
+        info = {}
+        if self.with_info:
+            info = {"gates_passed": rec["gates_passed"], "time_passed": rec["time_passed"]}
+            if self.debug_info:
+                dbg = h["dbg"].numpy()
+                info["next_gate_index"], info["events"] = dbg[:, 2], dbg[:, 3]
+        if self.float_flags:
+            term, trunc = term.astype(np.float32), trunc.astype(np.float32)
+        if self.copy_outputs:
+            obs, rew, term, trunc = obs.copy(), rew.copy(), term.copy(), trunc.copy()
+            info = {k: v.copy() for k, v in info.items()}
+        return obs, rew, term, trunc, info
 
     # ------------------------------------------------------------------ multi-step launch
     def rollout(self, actions: torch.Tensor, obs_out=None, reward_out=None, term_out=None, trunc_out=None,
@@ -337,8 +371,20 @@ class MultiTrackVecEnv:
         self.single_action_space = self.envs[0].single_action_space
 
     def reset(self, seed=None, options=None):
-        for env in self.envs:
-            env.reset(seed=seed)
+        """``options={"track_paths": [path_0, path_1, ...]}`` switches every group to a new track (one path per
+        group, CarEnv.reset(options={"track_path": ...}) per group, lib/car_env.py:621-628); any other option is
+        refused rather than silently ignored."""
+        paths = None
+        if options:
+            unknown = set(options) - {"track_paths"}
+            if unknown:
+                raise ValueError(f"MultiTrackVecEnv.reset does not understand options {sorted(unknown)}; "
+                                 "use options={'track_paths': [one path per group]}")
+            paths = list(options["track_paths"])
+            if len(paths) != len(self.envs):
+                raise ValueError(f"expected {len(self.envs)} track paths, got {len(paths)}")
+        for i, env in enumerate(self.envs):
+            env.reset(seed=seed, options={"track_path": paths[i]} if paths else None)
         zeros = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         return self._obs, {"gates_passed": zeros, "time_passed": zeros.clone()}
 

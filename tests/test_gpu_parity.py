@@ -82,13 +82,16 @@ def test_step_api_device_and_numpy_paths_agree_with_rollout(tracks_dir):
         o1, r1, te1, tr1, i1 = env_a.step(torch.from_numpy(acts[t]).cuda())          # int64 on device
         o2, r2, te2, tr2, i2 = env_b.step(acts[t])                                    # numpy in, numpy out
         assert o1.dtype == torch.float32 and te1.dtype == torch.bool and r1.dtype == torch.float32
-        assert isinstance(o2, np.ndarray) and te2.dtype == np.bool_
+        assert isinstance(o2, np.ndarray) and te2.dtype == np.bool_ and tr2.dtype == np.bool_
+        assert r2.dtype == np.float64 and o2.dtype == np.float32          # the reference's dtypes (lib/car_env.py:760)
         assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
         assert np.array_equal(te1.cpu().numpy(), te2) and np.array_equal(tr1.cpu().numpy(), tr2)
         assert np.array_equal(o2, ref["obs"][t].cpu().numpy())
         assert np.array_equal(r2, ref["reward"][t].cpu().numpy())
         assert np.array_equal(te2.astype(np.float32), ref["terminated"][t].cpu().numpy())
         assert np.array_equal(i2["gates_passed"], ref["info"]["gates_passed"][t].cpu().numpy())
+        assert np.array_equal(i2["time_passed"], ref["info"]["time_passed"][t].cpu().numpy())
+        assert set(i2) == {"gates_passed", "time_passed"}                 # the reference's info dict, nothing else
     assert ref["terminated"].sum() > 0
     # state arrays agree after T single steps and after one T-step launch
     assert torch.equal(env_a.pos, env_c.pos) and torch.equal(env_a.ints, env_c.ints)
@@ -642,3 +645,52 @@ def test_cuda_path_against_the_unmodified_reference(tracks_dir, tmp_path):
         out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
         assert_trajectory_matches(_gpu_traj(out), rec, what=f"{name} vs unmodified reference", rtol=tol)
         assert rec["term"].sum() > 0
+
+
+def test_numpy_step_records_debug_info_copy_outputs_and_device_records(tracks_dir):
+    """The numpy step ships one 16-byte record per env (carenv_step_host_records): debug_info=True adds
+    next_gate_index / events, copy_outputs=True returns arrays that survive the next step, and the device-buffer
+    variant carenv_step_records writes the same records."""
+    import ctypes as C
+    from ppo_car_b200 import _lib
+
+    path = os.path.join(tracks_dir, "big_track.json")
+    n = 70_001                                                    # 4 sub-ranges, ragged
+    rng = np.random.default_rng(3)
+    env_v = ppo_car_b200.VecCarEnv(n, path, debug_info=True)
+    env_c = ppo_car_b200.VecCarEnv(n, path, copy_outputs=True)
+    env_d = ppo_car_b200.VecCarEnv(n, path)
+    for e in (env_v, env_c, env_d):
+        e.reset()
+    rec_dev = torch.empty((n, 16), dtype=torch.uint8, device="cuda")
+    obs_dev = torch.empty((n, 18), dtype=torch.float32, device="cuda")
+    kept = None
+    for t in range(60):
+        a = rng.choice(9, size=n, p=[.3, .02, .1, .1, .2, .2, .02, .02, .04])
+        ov, rv, tev, trv, iv = env_v.step(a)
+        oc, rc_, tec, trc, ic = env_c.step(a)
+        od, rd, ted, trd, idd = env_d.step(torch.from_numpy(a).cuda())
+        assert np.array_equal(ov, oc) and np.array_equal(rv, rc_) and np.array_equal(tev, tec) and np.array_equal(trv, trc)
+        assert np.array_equal(ov, od.cpu().numpy()) and np.array_equal(rv, rd.cpu().numpy().astype(np.float64))
+        assert np.array_equal(iv["next_gate_index"], idd["next_gate_index"].cpu().numpy())
+        assert np.array_equal(iv["events"], idd["events"].cpu().numpy())
+        assert np.array_equal(iv["gates_passed"], ic["gates_passed"])
+        if kept is not None:                                      # copies of step t-1 were not overwritten by step t
+            assert np.array_equal(kept[0], kept[1]) and not np.array_equal(kept[0], oc)
+        kept = (oc, oc.copy())
+    # device records: same bytes as the host records of an identical env
+    env_r = ppo_car_b200.VecCarEnv(n, path)
+    env_r.reset()
+    env_h = ppo_car_b200.VecCarEnv(n, path)
+    env_h.reset()
+    a = rng.integers(0, 9, size=n)
+    L = _lib.lib()
+    ad = torch.from_numpy(a).cuda()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = L.carenv_step_records(env_r._handle, n, p(env_r.pos), p(env_r.vel), p(env_r.ints), p(ad), _lib.ACT_I64, 1.0,
+                               p(obs_dev), p(rec_dev), None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    oh, rh, teh, trh, ih = env_h.step(a)
+    rec = rec_dev.cpu().numpy().view(ppo_car_b200.VecCarEnv._REC_DTYPE).reshape(n)
+    assert np.array_equal(rec["reward"].astype(np.float64), rh) and np.array_equal(rec["terminated"], teh)
+    assert np.array_equal(rec["time_passed"], ih["time_passed"]) and np.array_equal(obs_dev.cpu().numpy(), oh)

@@ -88,7 +88,7 @@ int carenv_step(void *handle, int n_envs, double *pos, double *vel, int32_t *int
  * numpy actions in, numpy observations / rewards / flags out).  actions_host [n_envs] of action_dtype and the
  * *_host outputs (layouts as in carenv_step; info_host may be NULL) are host pointers; pinned memory
  * (carenv_host_alloc, or any cudaHostAlloc / torch pin_memory buffer) makes the copies asynchronous — the batch
- * is cut into sub-ranges of 16,384 or more environments (at most 16) on internal streams so that the device->host copy of one
+ * is cut into sub-ranges of 16,384 or more environments (at most 8) on internal streams so that the device->host copy of one
  * range overlaps the kernel and copies of the next.  The state arrays stay on the device.  The call is ordered
  * after earlier work on `stream`, later work on `stream` sees the new state, and it RETURNS WHEN THE RESULTS ARE
  * IN THE HOST BUFFERS.  The library owns the staging buffers (per handle, sized on first use). */
@@ -98,27 +98,23 @@ int carenv_step_host(void *handle, int n_envs, double *pos, double *vel, int32_t
 
 /* The same step with ONE 16-byte record per environment instead of three arrays (reward, terminated, truncated)
  * plus the info array: what the reference returns besides the observation (lib/car_env.py:760 reward and flags,
- * 599-603 the info dict) in the layout that costs the least PCIe traffic — 72 + 16 = 88 bytes per environment
- * and two device->host copies per sub-range.  numpy reads the fields as strided views of the record array.
+ * 599-603 the info dict), already in the reference's dtypes and in the layout that costs the least PCIe traffic —
+ * 72 + 16 = 88 bytes per environment and two device->host copies per sub-range, no conversion pass on the host.
+ * numpy reads the fields as strided views of the record array.
  *   rec_host         [n_envs] records (pinned memory recommended)
- *   reward64_host    [n_envs] float64 or NULL: the rewards widened to the dtype of the reference's numpy boundary
- *                    (a Python float per env -> float64), converted on the calling thread range by range while the
- *                    later ranges are still being copied
  *   debug_info_host  [n_envs][4] int32 or NULL: gates_passed, time_passed, next_gate_index, events (as info_out of
  *                    carenv_step; 16 more bytes per environment over PCIe — for parity tests, off by default)
  * carenv_step_records is the device-buffer variant (rec_out / debug_info_out are device pointers). */
 typedef struct carenv_step_record {
-    float reward;            /* float32(reward_f64 * reward_scale) */
+    double reward;           /* reward_f64 * reward_scale: the float64 TransformReward yields (train.py:65, 68) */
+    int32_t gates_passed;    /* info["gates_passed"] of the finished step (pre-reset), lib/car_env.py:599-603 */
+    uint16_t time_passed;    /* info["time_passed"], 1..1000 */
     uint8_t terminated;      /* lib/car_env.py:745-748 */
     uint8_t truncated;       /* lib/car_env.py:749-750 */
-    uint16_t pad;
-    int32_t gates_passed;    /* info["gates_passed"] of the finished step (pre-reset), lib/car_env.py:599-603 */
-    int32_t time_passed;     /* info["time_passed"] */
 } carenv_step_record;
 int carenv_step_host_records(void *handle, int n_envs, double *pos, double *vel, int32_t *ints,
                              const void *actions_host, int action_dtype, double reward_scale, float *obs_host,
-                             carenv_step_record *rec_host, double *reward64_host, int32_t *debug_info_host,
-                             void *stream);
+                             carenv_step_record *rec_host, int32_t *debug_info_host, void *stream);
 int carenv_step_records(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions,
                         int action_dtype, double reward_scale, float *obs_out, carenv_step_record *rec_out,
                         int32_t *debug_info_out, void *stream);

@@ -67,7 +67,7 @@ def lib():
     L.carenv_step.argtypes = [vp, i32, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp, i32, vp, vp]
     L.carenv_rollout.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp, i32, vp, vp]
     L.carenv_step_host.argtypes = L.carenv_step.argtypes
-    L.carenv_step_host_records.argtypes = [vp, i32, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp, vp]
+    L.carenv_step_host_records.argtypes = [vp, i32, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp]
     L.carenv_step_records.argtypes = [vp, i32, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp]
     L.carenv_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.carenv_host_free.argtypes = [vp]

@@ -126,6 +126,7 @@ struct EnvState {
 struct StepResult {
     float obs[kObsDim];
     float reward;       // float32(reward_f64 * reward_scale)
+    double reward64;    // reward_f64 * reward_scale: what TransformReward hands to the reference's numpy boundary
     int terminated, truncated;
     int gates_passed, time_passed, next_gate;   // info of the finished step (pre-reset)
     int gate_hit, lap;
@@ -666,7 +667,8 @@ CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackPar
     o.terminated = 0; o.truncated = 0;
     if (destroyed) { o.terminated = 1; reward = dsub(reward, 3.0); }
     else if (s.t >= kTimeLimit) o.truncated = 1;
-    o.reward = (float)dmul(reward, reward_scale);
+    o.reward64 = dmul(reward, reward_scale);
+    o.reward = (float)o.reward64;
     o.gates_passed = s.passed; o.time_passed = s.t; o.next_gate = s.next_gate;
 
     // Same-step autoreset.  The live observation is formed for every lane; the reset (state overwrite + the

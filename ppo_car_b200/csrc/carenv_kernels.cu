@@ -99,19 +99,6 @@ struct HostStep {
     }
 };
 
-// float32 rewards of a range of step records -> the float64 array the reference's numpy boundary returns
-// (lib/car_env.py:760: a Python float per env, stacked by the vector env into float64).  float -> double is exact.
-static void widen_rewards(const carenv_step_record *rec, double *out, int m) {
-    int i = 0;
-#if defined(__SSE2__)
-    for (; i + 2 <= m; i += 2) {
-        const __m128 v = _mm_set_ps(0.0f, 0.0f, rec[i + 1].reward, rec[i].reward);
-        _mm_storeu_pd(out + i, _mm_cvtps_pd(v));
-    }
-#endif
-    for (; i < m; ++i) out[i] = (double)rec[i].reward;
-}
-
 // int64 actions (what train.py:185 passes) -> one byte each; anything outside 0..8 acts like 8 (lib/car_env.py:698-722).
 // Runs on the host in front of every sub-range of carenv_step_host, so it is written for SSE2 (4 actions per
 // iteration, ~0.3 ns each) instead of a scalar 64-bit compare-and-select loop (1 ns each).
@@ -162,14 +149,15 @@ template <> __device__ __forceinline__ uint8_t make_flag<uint8_t>(int v) { retur
 template <> __device__ __forceinline__ float make_flag<float>(int v) { return v ? 1.0f : 0.0f; }
 
 // Reward / flags / info of one env-step: either the separate arrays of carenv_step / carenv_rollout or ONE 16-byte
-// carenv_step_record (reward f32 | terminated u8 | truncated u8 | pad u16 | gates_passed i32 | time_passed i32) —
-// what the host-buffer step path ships over PCIe.
+// carenv_step_record (reward f64 | gates_passed i32 | time_passed u16 | terminated u8 | truncated u8) — what the
+// host-buffer step path ships over PCIe, already in the reference's dtypes.
 template <typename FlagT>
 __device__ __forceinline__ void store_step(const StepResult &o, size_t idx, float *__restrict__ rew_out,
                                            FlagT *__restrict__ term_out, FlagT *__restrict__ trunc_out,
                                            int4 *__restrict__ info_out, int4 *__restrict__ rec_out) {
     if (rec_out) {
-        rec_out[idx] = make_int4(__float_as_int(o.reward), o.terminated | (o.truncated << 8), o.gates_passed, o.time_passed);
+        rec_out[idx] = make_int4(__double2loint(o.reward64), __double2hiint(o.reward64), o.gates_passed,
+                                 (o.time_passed & 0xffff) | (o.terminated << 16) | (o.truncated << 24));
     } else {
         rew_out[idx] = o.reward;
         term_out[idx] = make_flag<FlagT>(o.terminated);
@@ -335,10 +323,12 @@ k_rollout_tab(const __grid_constant__ TrackParams P, const Tables G, const float
     // blocks [0, n_main) hold epb_main environments each (full rounds: four warps per scheduler), the blocks of the
     // last round epb_last (a multiple of 128: every scheduler of the SM gets the same number of warps)
     for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        // (a last-round block is its CTA's final block, so leaving the loop is the same as skipping the block — and
+        // `break` keeps the loop body provably convergent, which the uniform-register operands of the wall tests need)
         const bool last = blk >= n_main;
-        if ((int)threadIdx.x >= (last ? epb_last : epb_main)) continue;
+        if ((int)threadIdx.x >= (last ? epb_last : epb_main)) break;
         const int e = last ? n_main * epb_main + (blk - n_main) * epb_last + threadIdx.x : blk * epb_main + threadIdx.x;
-        if (e >= n_envs) continue;
+        if (e >= n_envs) break;
         EnvState s;
         {
             const double2 p = pos[e], v = vel[e];
@@ -1225,12 +1215,11 @@ int carenv_host_free(void *ptr) {
 }
 
 // Shared implementation of the host-buffer steps.  `rec_host` != null: record mode (one 16-byte record per environment
-// instead of the reward / flag arrays; optionally `reward64_host`, widened on this thread range by range while the
-// later ranges are still in flight).
+// instead of the reward / flag arrays).
 static int step_host_impl(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions_host,
                           int action_dtype, double reward_scale, float *obs_host, float *reward_host, void *term_host,
                           void *trunc_host, int flag_dtype, int32_t *info_host, carenv_step_record *rec_host,
-                          double *reward64_host, void *stream) {
+                          void *stream) {
     Handle *h = static_cast<Handle *>(handle);
     if (!h) return fail(CARENV_E_INVAL, "null handle");
     if (n_envs < 0) return fail(CARENV_E_INVAL, "negative n_envs");
@@ -1264,11 +1253,12 @@ static int step_host_impl(void *handle, int n_envs, double *pos, double *vel, in
         if (e != cudaSuccess) { S.release(); return cuda_fail(e, "carenv_step_host: staging allocation"); }
         S.cap = n_envs; S.flag_bytes = fb;
     }
-    // Sub-ranges sized by bytes (16,384 environments = 1.4 MB of results, at most 16 ranges): the narrowing + H2D +
+    // Sub-ranges sized by bytes (16,384 environments = 1.4 MB of results, at most 8 ranges): the narrowing + H2D +
     // kernel of range i + 1 overlap the D2H copies of range i, which are the bottleneck (88 B per environment over
     // PCIe in record mode).  A 131,072-environment shard of an 8-GPU job gets an 8-deep pipeline, not a 2-deep one.
+    // Measured at 1,048,576 envs (benchmarks/e2e_breakdown.py): 2 ranges 2.05 ms, 4: 1.84, 8: 1.82, 16: 1.85.
     int n_ranges = n_envs / 16384;
-    n_ranges = n_ranges < 1 ? 1 : (n_ranges > HostStep::kMaxRanges ? HostStep::kMaxRanges : n_ranges);
+    n_ranges = n_ranges < 1 ? 1 : (n_ranges > 8 ? 8 : n_ranges);
     if (h->host_ranges > 0) n_ranges = h->host_ranges > HostStep::kMaxRanges ? HostStep::kMaxRanges : h->host_ranges;
     if (n_ranges > n_envs) n_ranges = n_envs;
     cudaStream_t user = static_cast<cudaStream_t>(stream);
@@ -1313,10 +1303,7 @@ static int step_host_impl(void *handle, int n_envs, double *pos, double *vel, in
         CU(cudaEventRecord(S.done[r], st));
     }
     for (int r = 0; r < n_ranges; ++r) CU(cudaStreamWaitEvent(user, S.done[r], 0));   // later device work sees the new state
-    for (int r = 0; r < n_ranges; ++r) {                                              // results are in the host buffers
-        CU(cudaEventSynchronize(S.done[r]));
-        if (rec_host && reward64_host) widen_rewards(rec_host + lo_of[r], reward64_host + lo_of[r], lo_of[r + 1] - lo_of[r]);
-    }
+    for (int r = 0; r < n_ranges; ++r) CU(cudaEventSynchronize(S.done[r]));           // results are in the host buffers
     return 0;
 }
 
@@ -1324,16 +1311,16 @@ int carenv_step_host(void *handle, int n_envs, double *pos, double *vel, int32_t
                      int action_dtype, double reward_scale, float *obs_host, float *reward_host, void *term_host,
                      void *trunc_host, int flag_dtype, int32_t *info_host, void *stream) {
     return step_host_impl(handle, n_envs, pos, vel, ints, actions_host, action_dtype, reward_scale, obs_host, reward_host,
-                          term_host, trunc_host, flag_dtype, info_host, nullptr, nullptr, stream);
+                          term_host, trunc_host, flag_dtype, info_host, nullptr, stream);
 }
 
 int carenv_step_host_records(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions_host,
                              int action_dtype, double reward_scale, float *obs_host, carenv_step_record *rec_host,
-                             double *reward64_host, int32_t *debug_info_host, void *stream) {
+                             int32_t *debug_info_host, void *stream) {
     if (!rec_host) return fail(CARENV_E_INVAL, "carenv_step_host_records needs rec_host");
     static_assert(sizeof(carenv_step_record) == 16, "record layout");
     return step_host_impl(handle, n_envs, pos, vel, ints, actions_host, action_dtype, reward_scale, obs_host, nullptr,
-                          nullptr, nullptr, CARENV_FLAG_U8, debug_info_host, rec_host, reward64_host, stream);
+                          nullptr, nullptr, CARENV_FLAG_U8, debug_info_host, rec_host, stream);
 }
 
 int carenv_step_records(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions,

@@ -188,22 +188,21 @@ class VecCarEnv:
             return self._obs.clone(), self._rew.clone(), term.clone(), trunc.clone(), self._info_dict(info)
         return self._obs, self._rew, term, trunc, self._info_dict(self._info)
 
-    _REC_DTYPE = np.dtype([("reward", "<f4"), ("terminated", "?"), ("truncated", "?"), ("pad", "<u2"),
-                           ("gates_passed", "<i4"), ("time_passed", "<i4")])      # carenv_step_record, 16 bytes
+    _REC_DTYPE = np.dtype([("reward", "<f8"), ("gates_passed", "<i4"), ("time_passed", "<u2"),
+                           ("terminated", "?"), ("truncated", "?")])              # carenv_step_record, 16 bytes
 
     def _step_host(self, actions: np.ndarray):
         """numpy in -> numpy out through carenv_step_host_records: the library narrows the actions into a pinned
         buffer and pipelines H2D copy, kernel and D2H copies over sub-ranges of the batch (the D2H copy is the
-        bottleneck: 88 B per env over PCIe — the observation and one 16-byte record); rewards are widened to the
-        reference's float64 on the host while later ranges are still in flight.  Flags and info are strided views
-        of the pinned record array (float_flags=True returns float32 copies instead)."""
+        bottleneck: 88 B per env over PCIe — the observation and one 16-byte record that already holds the float64
+        reward, the bool flags and the info counters).  Rewards, flags and info are strided views of the pinned
+        record array (float_flags=True returns float32 copies of the flags instead)."""
         n = self.num_envs
         if actions.size != n:
             raise ValueError(f"expected {n} actions, got {actions.size}")
         if self._host is None:
             pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
             self._host = dict(obs=pin((n, OBS_DIM), torch.float32), rec=pin((n, 16), torch.uint8),
-                              rew64=pin((n,), torch.float64),
                               dbg=pin((n, 4), torch.int32) if self.debug_info else None)
         h = self._host
         flat = np.ascontiguousarray(actions.reshape(-1))
@@ -217,11 +216,10 @@ class VecCarEnv:
         with torch.cuda.device(self.device):
             rc = self._L.carenv_step_host_records(self._handle, n, _ptr(self.pos), _ptr(self.vel), _ptr(self.ints),
                                                   C.c_void_p(flat.ctypes.data), code, self.reward_scaling,
-                                                  _ptr(h["obs"]), _ptr(h["rec"]), _ptr(h["rew64"]), _ptr(h["dbg"]),
-                                                  self._stream())
+                                                  _ptr(h["obs"]), _ptr(h["rec"]), _ptr(h["dbg"]), self._stream())
         _lib.check(rc, "carenv_step_host_records")
         rec = h["rec"].numpy().view(self._REC_DTYPE).reshape(n)
-        obs, rew, term, trunc = h["obs"].numpy(), h["rew64"].numpy(), rec["terminated"], rec["truncated"]
+        obs, rew, term, trunc = h["obs"].numpy(), rec["reward"], rec["terminated"], rec["truncated"]
         info = {}
         if self.with_info:
             info = {"gates_passed": rec["gates_passed"], "time_passed": rec["time_passed"]}

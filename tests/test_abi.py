@@ -70,7 +70,7 @@ def test_bad_arguments_return_error_codes():
     assert L.carenv_rollout_poses(None, 1, 1, None, None, None, None, 0, 1.0, None, None, None, None, 0, None, None) < 0
     assert L.carenv_observe(None, 1, None, None, None, None) == -1
     assert L.carenv_step_host(None, 1, None, None, None, None, 0, 1.0, None, None, None, None, 0, None, None) == -1
-    assert L.carenv_step_host_records(None, 1, None, None, None, None, 0, 1.0, None, None, None, None, None) == -1
+    assert L.carenv_step_host_records(None, 1, None, None, None, None, 0, 1.0, None, None, None, None) == -1
     assert L.carenv_step_records(None, 1, None, None, None, None, 0, 1.0, None, None, None, None) == -1
     assert L.carenv_host_alloc(16, None) == -1 and L.carenv_host_free(None) == 0
 

@@ -84,10 +84,10 @@ def test_step_api_device_and_numpy_paths_agree_with_rollout(tracks_dir):
         assert o1.dtype == torch.float32 and te1.dtype == torch.bool and r1.dtype == torch.float32
         assert isinstance(o2, np.ndarray) and te2.dtype == np.bool_ and tr2.dtype == np.bool_
         assert r2.dtype == np.float64 and o2.dtype == np.float32          # the reference's dtypes (lib/car_env.py:760)
-        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2.astype(np.float32))
         assert np.array_equal(te1.cpu().numpy(), te2) and np.array_equal(tr1.cpu().numpy(), tr2)
         assert np.array_equal(o2, ref["obs"][t].cpu().numpy())
-        assert np.array_equal(r2, ref["reward"][t].cpu().numpy())
+        assert np.array_equal(r2.astype(np.float32), ref["reward"][t].cpu().numpy())
         assert np.array_equal(te2.astype(np.float32), ref["terminated"][t].cpu().numpy())
         assert np.array_equal(i2["gates_passed"], ref["info"]["gates_passed"][t].cpu().numpy())
         assert np.array_equal(i2["time_passed"], ref["info"]["time_passed"][t].cpu().numpy())
@@ -208,7 +208,7 @@ def test_host_step_pipeline_large_batch(tracks_dir):
             ih = {k: v.cpu().numpy() for k, v in ih.items()}
         else:
             oh, rh, teh, trh, ih = env_h.step(a)
-        assert np.array_equal(oh, od.cpu().numpy()) and np.array_equal(rh, rd.cpu().numpy())
+        assert np.array_equal(oh, od.cpu().numpy()) and np.array_equal(np.asarray(rh, np.float32), rd.cpu().numpy())
         assert np.array_equal(teh, ted.cpu().numpy()) and np.array_equal(trh, trd.cpu().numpy())
         assert np.array_equal(ih["gates_passed"], idd["gates_passed"].cpu().numpy())
     assert torch.equal(env_h.pos, env_d.pos) and torch.equal(env_h.ints, env_d.ints)
@@ -645,6 +645,13 @@ def test_cuda_path_against_the_unmodified_reference(tracks_dir, tmp_path):
         out = env.rollout(torch.from_numpy(acts).cuda(), store_info=True)
         assert_trajectory_matches(_gpu_traj(out), rec, what=f"{name} vs unmodified reference", rtol=tol)
         assert rec["term"].sum() > 0
+        # the numpy boundary: float64 rewards equal to TransformReward's r * 0.1 (train.py:65, 68) bit for bit
+        env2 = ppo_car_b200.VecCarEnv(n, our_path, reward_scaling=0.1)
+        env2.reset()
+        for t in range(min(T, 40)):
+            o, r, te, tr, info = env2.step(acts[t].astype(np.int64))
+            assert r.dtype == np.float64 and np.array_equal(r, rec["rew"][t] * 0.1), (name, t)
+            assert np.array_equal(te, rec["term"][t]) and np.array_equal(info["time_passed"], rec["time_passed"][t])
 
 
 def test_numpy_step_records_debug_info_copy_outputs_and_device_records(tracks_dir):
@@ -671,7 +678,7 @@ def test_numpy_step_records_debug_info_copy_outputs_and_device_records(tracks_di
         oc, rc_, tec, trc, ic = env_c.step(a)
         od, rd, ted, trd, idd = env_d.step(torch.from_numpy(a).cuda())
         assert np.array_equal(ov, oc) and np.array_equal(rv, rc_) and np.array_equal(tev, tec) and np.array_equal(trv, trc)
-        assert np.array_equal(ov, od.cpu().numpy()) and np.array_equal(rv, rd.cpu().numpy().astype(np.float64))
+        assert np.array_equal(ov, od.cpu().numpy()) and np.array_equal(rv.astype(np.float32), rd.cpu().numpy())
         assert np.array_equal(iv["next_gate_index"], idd["next_gate_index"].cpu().numpy())
         assert np.array_equal(iv["events"], idd["events"].cpu().numpy())
         assert np.array_equal(iv["gates_passed"], ic["gates_passed"])
@@ -692,5 +699,5 @@ def test_numpy_step_records_debug_info_copy_outputs_and_device_records(tracks_di
     assert rc == 0
     oh, rh, teh, trh, ih = env_h.step(a)
     rec = rec_dev.cpu().numpy().view(ppo_car_b200.VecCarEnv._REC_DTYPE).reshape(n)
-    assert np.array_equal(rec["reward"].astype(np.float64), rh) and np.array_equal(rec["terminated"], teh)
+    assert np.array_equal(rec["reward"], rh) and rec["reward"].dtype == np.float64 and np.array_equal(rec["terminated"], teh)
     assert np.array_equal(rec["time_passed"], ih["time_passed"]) and np.array_equal(obs_dev.cpu().numpy(), oh)

@@ -84,6 +84,13 @@ int carenv_step(void *handle, int n_envs, double *pos, double *vel, int32_t *int
                 int action_dtype, double reward_scale, float *obs_out, float *reward_out, void *term_out,
                 void *trunc_out, int flag_dtype, int32_t *info_out, void *stream);
 
+/* carenv_step that also returns the observation of the state each step ENDED in, before the autoreset — gymnasium's
+ * info["final_observation"] (AsyncVectorEnv worker; train.py:185 discards it, value-bootstrapping users need
+ * it).  final_obs_out [n_envs][18] float32 equals obs_out wherever the episode did not end. */
+int carenv_step_final(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions,
+                      int action_dtype, double reward_scale, float *obs_out, float *final_obs_out, float *reward_out,
+                      void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream);
+
 /* carenv_step with HOST buffers — what the reference's rollout loop does around envs.step (train.py:185-192:
  * numpy actions in, numpy observations / rewards / flags out).  actions_host [n_envs] of action_dtype and the
  * *_host outputs (layouts as in carenv_step; info_host may be NULL) are host pointers; pinned memory
@@ -140,6 +147,28 @@ int carenv_rollout_poses(void *handle, int n_envs, int n_steps, double *pos, dou
                          const void *actions, int action_dtype, double reward_scale, void *pose_out, float *reward_out,
                          void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream);
 int carenv_observe(void *handle, long long n, const void *poses, const long long *index, float *obs_out, void *stream);
+
+/* Several tracks in ONE launch — CarEnv.reset(options={"track_path": ...}) per environment (lib/car_env.py:621-628):
+ * `handles` are n_tracks handles from carenv_create (they own the per-track tables and must outlive `multi`);
+ * track_ids [n_envs] int32 (device) selects every environment's track; carenv_multi_reset / carenv_multi_rollout are
+ * carenv_reset / carenv_rollout with that extra argument (n_steps = 1 is a step).  Environments of different tracks
+ * may be mixed freely; results are bit-identical to stepping each environment in a single-track handle. */
+int carenv_multi_create(void *const *handles, int n_tracks, void **multi);
+int carenv_multi_destroy(void *multi);
+int carenv_multi_reset(void *multi, int n_envs, const int32_t *track_ids, double *pos, double *vel, int32_t *ints,
+                       float *obs_out, void *stream);
+int carenv_multi_rollout(void *multi, int n_envs, int n_steps, const int32_t *track_ids, double *pos, double *vel,
+                         int32_t *ints, const void *actions, int action_dtype, double reward_scale, float *obs_out,
+                         float *reward_out, void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out,
+                         void *stream);
+
+/* Headless render_mode="rgb_array" frames (CarEnv.render / __render_frame, lib/car_env.py:762-812; consumer: the video
+ * logger train.py:23-50) for n_frames environments env_index[f] (device int32): rgb_out [n_frames][height][width][3]
+ * uint8 — background, corridor, walls, active gates (the next one yellow), rays and the car as a box (the reference
+ * blits a sprite).  width x height = 1280 x 720 is the reference's canvas; n_outer_segments = how many of the
+ * handle's wall segments belong to the outer polygon.  A diagnostic picture, not a pixel-exact copy of pygame. */
+int carenv_render(void *handle, int n_outer_segments, int n_frames, const int32_t *env_index, const double *pos,
+                  const int32_t *ints, const float *obs, int width, int height, unsigned char *rgb_out, void *stream);
 
 /* Options.  "pose_rows" = 1: the fused rollout kernels below write 32-byte pose records (see
  * carenv_rollout_poses) through their obs_buf argument instead of observations.  Tuning / test hooks:

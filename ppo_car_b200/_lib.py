@@ -69,6 +69,12 @@ def lib():
     L.carenv_step_host.argtypes = L.carenv_step.argtypes
     L.carenv_step_host_records.argtypes = [vp, i32, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp]
     L.carenv_step_records.argtypes = [vp, i32, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp]
+    L.carenv_step_final.argtypes = [vp, i32, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp, vp, i32, vp, vp]
+    L.carenv_multi_create.argtypes = [vp, i32, C.POINTER(vp)]
+    L.carenv_multi_destroy.argtypes = [vp]
+    L.carenv_multi_reset.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    L.carenv_multi_rollout.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, f64, vp, vp, vp, vp, i32, vp, vp]
+    L.carenv_render.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp]
     L.carenv_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.carenv_host_free.argtypes = [vp]
     L.carenv_rollout_poses.argtypes = L.carenv_rollout.argtypes
@@ -94,7 +100,8 @@ def lib():
     L.carenv_policy_weights_floats_tc.restype = i32
     L.carenv_policy_rollout_tc.argtypes = L.carenv_policy_rollout.argtypes
     for name in ("carenv_create", "carenv_destroy", "carenv_reset_obs", "carenv_reset", "carenv_step",
-                 "carenv_rollout", "carenv_rollout_poses", "carenv_observe", "carenv_step_host", "carenv_step_host_records", "carenv_step_records", "carenv_host_alloc", "carenv_host_free", "carenv_stats", "gae_reverse_scan", "carenv_bench_ffma", "carenv_set_option", "carenv_policy_rollout", "carenv_policy_rollout_tc"):
+                 "carenv_rollout", "carenv_rollout_poses", "carenv_observe", "carenv_step_host", "carenv_step_host_records", "carenv_step_records", "carenv_step_final", "carenv_multi_create", "carenv_multi_destroy", "carenv_multi_reset",
+                 "carenv_multi_rollout", "carenv_render", "carenv_host_alloc", "carenv_host_free", "carenv_stats", "gae_reverse_scan", "carenv_bench_ffma", "carenv_set_option", "carenv_policy_rollout", "carenv_policy_rollout_tc"):
         getattr(L, name).restype = i32
     if L.carenv_abi_version() != 1:
         raise CarEnvError("libcarenv_b200.so ABI version mismatch; rebuild")

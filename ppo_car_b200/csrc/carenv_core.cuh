@@ -640,9 +640,12 @@ CE_HD void pose_observation(const EnvState &s, float vx10, float vy10, const flo
 }
 
 // ---- one CarEnv.step with same-step autoreset --------------------------------------------------
+// `final_obs` (optional, 18 floats): receives the observation of the state the step ended in BEFORE the autoreset —
+// gymnasium's info["final_observation"]; it equals o.obs wherever the episode did not end.
 template <int U, bool TAB = false>
 CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackParams &P, const Tables &T,
-                    StepResult &o, unsigned long long *stats, const WarpSeg *ws = nullptr, const TabView *tv = nullptr) {
+                    StepResult &o, unsigned long long *stats, const WarpSeg *ws = nullptr, const TabView *tv = nullptr,
+                    float *final_obs = nullptr) {
     int thrust, turn;
     decode_action(action, thrust, turn);
     double reward = thrust > 0 ? 0.01 : 0.0;
@@ -675,6 +678,10 @@ CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackPar
     // constant reset observation, ~40 select instructions) sits behind a warp vote: an episode ends in about 0.4 %
     // of env-steps, i.e. seven of eight warp-steps skip it with one uniform branch.
     pose_observation(s, (float)dmul(s.vx, 0.1), (float)dmul(s.vy, 0.1), dist, T, o.obs);
+    if (final_obs) {
+#pragma unroll
+        for (int i = 0; i < kObsDim; ++i) final_obs[i] = o.obs[i];
+    }
     const bool done = (o.terminated | o.truncated) != 0;
 #if defined(__CUDA_ARCH__)
     if (__any_sync(__activemask(), done))

@@ -27,6 +27,7 @@
 #endif
 
 #include <string>
+#include <vector>
 
 #include "../../include/carenv_b200.h"
 #include "carenv_tables.h"
@@ -60,6 +61,7 @@ struct Handle {
     unsigned char *d_blob;    // trig64 | acc64 | gates | trig32 | trig32s | walls64 | segf | segd | den4
     const float4 *d_den4;     // [72][n_pairs] denominators of the pair kernels (null: track without pairs)
     int host_ranges;          // tuning hook: sub-ranges of the host-buffer step (0 = by size)
+    float *cur_fobs;          // pre-reset ("final") observations for the launch being dispatched (else null)
     int4 *cur_rec;            // step records instead of reward / flag arrays for the launch being dispatched (else null)
     int tab;                  // 0 = k_rollout_tab for large launches, 1 = always (where the track allows), -1 = never
     Tables dev;               // device pointers into d_blob
@@ -253,7 +255,7 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
           double2 *__restrict__ vel, int4 *__restrict__ ints, const ActT *__restrict__ actions, double reward_scale,
           float *__restrict__ obs_out, float *__restrict__ rew_out, FlagT *__restrict__ term_out,
           FlagT *__restrict__ trunc_out, int4 *__restrict__ info_out, int4 *__restrict__ rec_out,
-          unsigned long long *stats, int obs_mode) {
+          float *__restrict__ fobs_out, unsigned long long *stats, int obs_mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -272,7 +274,7 @@ k_rollout(const __grid_constant__ TrackParams P, const Tables G, int n_envs, int
         const int a = a_next;
         if (t + 1 < n_steps) a_next = (int)actions[idx + (size_t)n_envs];   // next step's action is in flight during this step
         StepResult o;
-        env_step<U>(s, a, reward_scale, P, T, o, stats);
+        env_step<U>(s, a, reward_scale, P, T, o, stats, nullptr, nullptr, fobs_out ? fobs_out + idx * kObsDim : nullptr);
         if (obs_mode == kObsFull) {
             float2 *dst = reinterpret_cast<float2 *>(obs_out + idx * kObsDim);
 #pragma unroll
@@ -369,7 +371,7 @@ k_rollout_warp(const __grid_constant__ TrackParams P, const Tables G, int n_envs
                double2 *__restrict__ vel, int4 *__restrict__ ints, const ActT *__restrict__ actions,
                double reward_scale, float *__restrict__ obs_out, float *__restrict__ rew_out,
                FlagT *__restrict__ term_out, FlagT *__restrict__ trunc_out, int4 *__restrict__ info_out,
-               int4 *__restrict__ rec_out, unsigned long long *stats, int obs_mode) {
+               int4 *__restrict__ rec_out, float *__restrict__ fobs_out, unsigned long long *stats, int obs_mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);
     const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -394,7 +396,8 @@ k_rollout_warp(const __grid_constant__ TrackParams P, const Tables G, int n_envs
         const int a = a_next;
         if (t + 1 < n_steps) a_next = (int)actions[idx + (size_t)n_envs];
         StepResult o;
-        env_step<kWarpPerEnv>(s, a, reward_scale, P, T, o, my_stats, &ws);
+        env_step<kWarpPerEnv>(s, a, reward_scale, P, T, o, my_stats, &ws, nullptr,
+                              (fobs_out && lane == 0) ? fobs_out + idx * kObsDim : nullptr);
         if (lane == 0) {
             if (obs_mode == kObsFull) {
                 float2 *dst = reinterpret_cast<float2 *>(obs_out + idx * kObsDim);
@@ -922,6 +925,131 @@ k_gae(const float *__restrict__ rew, const float *__restrict__ val, const float 
   }
 }
 
+// ---- several tracks in ONE launch (reset(options={"track_path": ...}) per environment,
+// lib/car_env.py:621-628).  Every environment carries a track id; the per-track constants (TrackParams) and tables
+// live in global memory (concatenated in the multi-track handle) and each thread reads ITS track's through a
+// pointer, so environments on different tracks may share a warp.  The arithmetic is the generic segment loop
+// (env_step<0>: geometry read through Tables::segf / segd), bit-identical to the single-track kernels.
+struct MultiTrack {
+    int n_tracks, device;
+    TrackParams *d_params;    // [n_tracks]
+    Tables *d_tables;         // [n_tracks] pointers into the single-track handles' blobs
+    unsigned long long *d_stats;
+};
+
+template <typename ActT, typename FlagT>
+__global__ void __launch_bounds__(128)
+k_rollout_multi(const TrackParams *__restrict__ params, const Tables *__restrict__ tables, int n_tracks,
+                const int *__restrict__ track_ids, int n_envs, int n_steps, double2 *__restrict__ pos,
+                double2 *__restrict__ vel, int4 *__restrict__ ints, const ActT *__restrict__ actions,
+                double reward_scale, float *__restrict__ obs_out, float *__restrict__ rew_out,
+                FlagT *__restrict__ term_out, FlagT *__restrict__ trunc_out, int4 *__restrict__ info_out,
+                unsigned long long *stats) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+    int tr = track_ids[e];
+    tr = tr < 0 ? 0 : (tr >= n_tracks ? n_tracks - 1 : tr);
+    const TrackParams &P = params[tr];
+    const Tables T = tables[tr];
+    EnvState s;
+    {
+        const double2 p = pos[e], v = vel[e];
+        const int4 q = ints[e];
+        s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
+        s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
+    }
+    for (int t = 0; t < n_steps; ++t) {
+        const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+        StepResult o;
+        env_step<0>(s, (int)actions[idx], reward_scale, P, T, o, stats);
+        if (obs_out) {
+            float2 *dst = reinterpret_cast<float2 *>(obs_out + idx * kObsDim);
+#pragma unroll
+            for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(o.obs[2 * i], o.obs[2 * i + 1]);
+        }
+        store_step(o, idx, rew_out, term_out, trunc_out, info_out, (int4 *)nullptr);
+    }
+    pos[e] = make_double2(s.px, s.py);
+    vel[e] = make_double2(s.vx, s.vy);
+    ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+}
+
+__global__ void __launch_bounds__(128)
+k_reset_multi(const TrackParams *__restrict__ params, int n_tracks, const int *__restrict__ track_ids, int n_envs,
+              double2 *__restrict__ pos, double2 *__restrict__ vel, int4 *__restrict__ ints, float *__restrict__ obs_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+    int tr = track_ids[e];
+    tr = tr < 0 ? 0 : (tr >= n_tracks ? n_tracks - 1 : tr);
+    const TrackParams &P = params[tr];
+    pos[e] = make_double2(P.start_x, P.start_y);
+    vel[e] = make_double2(0.0, 0.0);
+    ints[e] = make_int4(0, 0, 0, 0);
+    if (obs_out)
+        for (int i = 0; i < kObsDim; ++i) obs_out[(size_t)e * kObsDim + i] = P.reset_obs[i];
+}
+
+// ---- headless rgb_array frames (lib/car_env.py:762-812, consumer train.py:23-50): one thread per pixel.
+// Background (11,102,35), the corridor between the outer and the inner polygon gray, walls black 5 px, active gates
+// green 5 px (the next one yellow), the rays as thin lines to their hit points, the car as a rotated 40 x 20 px box
+// (the reference blits lib/assets/car.png there; the sprite is not part of this repository).  A diagnostic picture
+// for videos of a handful of environments — not a pixel-exact restatement of pygame's rasteriser.
+__device__ __forceinline__ float seg_dist2(float px, float py, float ax, float ay, float bx, float by) {
+    const float ex = bx - ax, ey = by - ay, wx = px - ax, wy = py - ay;
+    const float l2 = ex * ex + ey * ey;
+    float t = l2 > 0.0f ? (wx * ex + wy * ey) / l2 : 0.0f;
+    t = fminf(fmaxf(t, 0.0f), 1.0f);
+    const float dx = wx - t * ex, dy = wy - t * ey;
+    return dx * dx + dy * dy;
+}
+
+__global__ void __launch_bounds__(256)
+k_render(const __grid_constant__ TrackParams P, const Tables G, int n_outer, int n_frames, const int *__restrict__ env_index,
+         const double2 *__restrict__ pos, const int4 *__restrict__ ints, const float *__restrict__ obs, int width,
+         int height, unsigned char *__restrict__ rgb) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (pix >= width * height || f >= n_frames) return;
+    const int e = env_index[f];
+    const float x = (float)(pix % width) + 0.5f, y = (float)(pix / width) + 0.5f;
+    const double2 cp = pos[e];
+    const int4 st = ints[e];
+    const float cx = (float)cp.x, cy = (float)cp.y;
+    const F2 hd = G.trig32[st.x];
+    // crossing number of the two closed border polylines; distance to the nearest wall
+    bool in_outer = false, in_inner = false;
+    float wall2 = 1.0e30f;
+    for (int j = 0; j < P.n_seg; ++j) {
+        const float ax = (float)G.walls64[4 * j], ay = (float)G.walls64[4 * j + 1];
+        const float bx = (float)G.walls64[4 * j + 2], by = (float)G.walls64[4 * j + 3];
+        if ((ay > y) != (by > y) && x < ax + (y - ay) * (bx - ax) / (by - ay)) {
+            if (j < n_outer) in_outer = !in_outer; else in_inner = !in_inner;
+        }
+        wall2 = fminf(wall2, seg_dist2(x, y, ax, ay, bx, by));
+    }
+    unsigned char r = 11, g = 102, b = 35;                                   // canvas.fill((11, 102, 35))
+    if (in_outer && !in_inner) { r = 190; g = 190; b = 190; }                // "gray" polygon minus the inner one
+    if (wall2 <= 6.25f) { r = 0; g = 0; b = 0; }                             // boundary.draw(canvas, "black", 5)
+    for (int q = st.z; q < P.n_gates; ++q) {                                 // gates below next_gate_index are inactive
+        const GateRec gt = G.gates[q];
+        if (seg_dist2(x, y, (float)gt.x1, (float)gt.y1, (float)gt.x2, (float)gt.y2) <= 6.25f) {
+            if (q == st.z) { r = 255; g = 255; b = 0; } else { r = 0; g = 255; b = 0; }
+        }
+    }
+    for (int i = 0; i < kNumRays; ++i) {                                     // car.draw_rays: origin -> hit point
+        const F2 d = G.trig32[wrap72(st.x + 6 * i)];
+        const float len = obs[(size_t)e * kObsDim + 6 + i] * 1000.0f;
+        if (seg_dist2(x, y, cx, cy, cx + d.x * len, cy + d.y * len) <= 0.6f) { r = 255; g = 255; b = 255; }
+    }
+    {   // the car: 40 x 20 px box along the heading
+        const float dx = x - cx, dy = y - cy;
+        const float u = dx * hd.x + dy * hd.y, v = -dx * hd.y + dy * hd.x;
+        if (fabsf(u) <= 20.0f && fabsf(v) <= 10.0f) { r = 200; g = 30; b = 30; if (u > 12.0f) { r = 250; g = 220; b = 60; } }
+    }
+    unsigned char *dst = rgb + ((size_t)f * width * height + pix) * 3;
+    dst[0] = r; dst[1] = g; dst[2] = b;
+}
+
 // FP32-pipe peak probe: kFfmaChains independent FFMA chains per thread, no memory traffic.
 // MEASURED_PEAKS.json has no FP32 entry, so bench.py measures one beside the nominal.
 constexpr int kFfmaChains = 8;
@@ -955,7 +1083,7 @@ int launch_rollout_t(Handle *h, int n_envs, int n_steps, double *pos, double *ve
         h->host.P, h->dev, n_envs, n_steps, reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel),
         reinterpret_cast<int4 *>(ints), static_cast<const ActT *>(actions), reward_scale, obs_out, reward_out,
         static_cast<FlagT *>(term_out), static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out),
-        h->cur_rec, h->d_stats, obs_mode);
+        h->cur_rec, h->cur_fobs, h->d_stats, obs_mode);
     CU(cudaGetLastError());
     return 0;
 }
@@ -1019,7 +1147,7 @@ int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel,
             h->host.P, h->dev, n_envs, n_steps, reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel),
             reinterpret_cast<int4 *>(ints), static_cast<const ActT *>(actions), reward_scale, obs_out, reward_out,
             static_cast<FlagT *>(term_out), static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out),
-            h->cur_rec, h->d_stats, obs_mode);
+            h->cur_rec, h->cur_fobs, h->d_stats, obs_mode);
         CU(cudaGetLastError());
         return 0;
     }
@@ -1028,7 +1156,7 @@ int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel,
     if (h->host.P.n_seg > kMaxSeg) U = 0;                   // geometry from shared memory
     // large launches: denominators from the shared-memory table (k_rollout_tab).  "Large" = at least two warps per
     // scheduler on every SM and enough steps to amortise staging the table copies (147 KB per CTA on big_track).
-    if (U >= 2 && h->d_den4 && h->tab >= 0 &&
+    if (U >= 2 && h->d_den4 && h->tab >= 0 && !h->cur_fobs &&
         (h->tab == 1 || (n_envs >= 148 * 384 && (long long)n_envs * n_steps >= (1LL << 22)))) {
         const int rc = launch_rollout_tab<ActT, FlagT>(h, U, n_envs, n_steps, pos, vel, ints, actions, reward_scale,
                                                        obs_out, reward_out, term_out, trunc_out, info_out, stream,
@@ -1093,7 +1221,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0; h->warp_per_env = 0; h->hs = nullptr; h->d_den4 = nullptr; h->tab = 0; h->cur_rec = nullptr; h->host_ranges = 0;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0; h->warp_per_env = 0; h->hs = nullptr; h->d_den4 = nullptr; h->tab = 0; h->cur_rec = nullptr; h->cur_fobs = nullptr; h->host_ranges = 0;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -1183,6 +1311,19 @@ int carenv_step(void *handle, int n_envs, double *pos, double *vel, int32_t *int
     if (!obs_out) return fail(CARENV_E_INVAL, "carenv_step needs obs_out");
     return dispatch_rollout(handle, n_envs, 1, pos, vel, ints, actions, action_dtype, reward_scale, obs_out,
                             reward_out, term_out, trunc_out, flag_dtype, info_out, stream, kObsFull);
+}
+
+int carenv_step_final(void *handle, int n_envs, double *pos, double *vel, int32_t *ints, const void *actions,
+                      int action_dtype, double reward_scale, float *obs_out, float *final_obs_out, float *reward_out,
+                      void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out, void *stream) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(CARENV_E_INVAL, "null handle");
+    if (!obs_out || !final_obs_out) return fail(CARENV_E_INVAL, "carenv_step_final needs obs_out and final_obs_out");
+    h->cur_fobs = final_obs_out;
+    const int rc = dispatch_rollout(handle, n_envs, 1, pos, vel, ints, actions, action_dtype, reward_scale, obs_out,
+                                    reward_out, term_out, trunc_out, flag_dtype, info_out, stream, kObsFull);
+    h->cur_fobs = nullptr;
+    return rc;
 }
 
 int carenv_rollout(void *handle, int n_envs, int n_steps, double *pos, double *vel, int32_t *ints,
@@ -1521,6 +1662,121 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
     if (U == 4) return launch(k_policy_rollout_tc<4, 2>);
     if (U == 2) return launch(k_policy_rollout_tc<2, 2>);
     return launch(k_policy_rollout_tc<1, 2>);
+}
+
+/* ---- several tracks in one launch ---- */
+int carenv_multi_create(void *const *handles, int n_tracks, void **multi) {
+    if (!multi) return fail(CARENV_E_INVAL, "null pointer");
+    *multi = nullptr;
+    if (!handles || n_tracks < 1 || n_tracks > 4096) return fail(CARENV_E_INVAL, "need 1..4096 track handles");
+    std::vector<TrackParams> params((size_t)n_tracks);
+    std::vector<Tables> tabs((size_t)n_tracks);
+    int device = -1;
+    for (int i = 0; i < n_tracks; ++i) {
+        const Handle *h = static_cast<const Handle *>(handles[i]);
+        if (!h) return fail(CARENV_E_INVAL, "null track handle");
+        if (device >= 0 && h->device != device) return fail(CARENV_E_INVAL, "all track handles must be on one device");
+        device = h->device;
+        params[i] = h->host.P;
+        tabs[i] = h->dev;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select CUDA device");
+    MultiTrack *m = new MultiTrack{n_tracks, device, nullptr, nullptr, nullptr};
+    cudaError_t e = cudaMalloc(&m->d_params, sizeof(TrackParams) * n_tracks);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_tables, sizeof(Tables) * n_tracks);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_stats, sizeof(unsigned long long) * kNumStats);
+    if (e == cudaSuccess) e = cudaMemset(m->d_stats, 0, sizeof(unsigned long long) * kNumStats);
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_params, params.data(), sizeof(TrackParams) * n_tracks, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_tables, tabs.data(), sizeof(Tables) * n_tracks, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(m->d_params); cudaFree(m->d_tables); cudaFree(m->d_stats);
+        delete m;
+        return cuda_fail(e, "carenv_multi_create");
+    }
+    *multi = m;
+    return 0;
+}
+
+int carenv_multi_destroy(void *multi) {
+    MultiTrack *m = static_cast<MultiTrack *>(multi);
+    if (!m) return 0;
+    {
+        DeviceGuard guard(m->device);
+        cudaFree(m->d_params); cudaFree(m->d_tables); cudaFree(m->d_stats);
+    }
+    delete m;
+    return 0;
+}
+
+int carenv_multi_reset(void *multi, int n_envs, const int32_t *track_ids, double *pos, double *vel, int32_t *ints,
+                       float *obs_out, void *stream) {
+    MultiTrack *m = static_cast<MultiTrack *>(multi);
+    if (!m) return fail(CARENV_E_INVAL, "null handle");
+    if (n_envs < 0) return fail(CARENV_E_INVAL, "negative n_envs");
+    if (n_envs == 0) return 0;
+    if (!track_ids || !pos || !vel || !ints) return fail(CARENV_E_INVAL, "null pointer");
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    k_reset_multi<<<(n_envs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        m->d_params, m->n_tracks, track_ids, n_envs, reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel),
+        reinterpret_cast<int4 *>(ints), obs_out);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int carenv_multi_rollout(void *multi, int n_envs, int n_steps, const int32_t *track_ids, double *pos, double *vel,
+                         int32_t *ints, const void *actions, int action_dtype, double reward_scale, float *obs_out,
+                         float *reward_out, void *term_out, void *trunc_out, int flag_dtype, int32_t *info_out,
+                         void *stream) {
+    MultiTrack *m = static_cast<MultiTrack *>(multi);
+    if (!m) return fail(CARENV_E_INVAL, "null handle");
+    if (n_envs < 0 || n_steps < 0) return fail(CARENV_E_INVAL, "negative n_envs / n_steps");
+    if (n_envs == 0 || n_steps == 0) return 0;
+    if (!track_ids || !pos || !vel || !ints || !actions || !reward_out || !term_out || !trunc_out)
+        return fail(CARENV_E_INVAL, "null pointer");
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = (n_envs + 127) / 128;
+#define MCASE(A, AT, F, FT)                                                                                         \
+    if (action_dtype == A && flag_dtype == F) {                                                                     \
+        k_rollout_multi<AT, FT><<<grid, 128, 0, st>>>(                                                              \
+            m->d_params, m->d_tables, m->n_tracks, track_ids, n_envs, n_steps, reinterpret_cast<double2 *>(pos),    \
+            reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints), static_cast<const AT *>(actions),     \
+            reward_scale, obs_out, reward_out, static_cast<FT *>(term_out), static_cast<FT *>(trunc_out),           \
+            reinterpret_cast<int4 *>(info_out), m->d_stats);                                                        \
+        CU(cudaGetLastError());                                                                                     \
+        return 0;                                                                                                   \
+    }
+    MCASE(CARENV_ACT_U8, uint8_t, CARENV_FLAG_U8, uint8_t)
+    MCASE(CARENV_ACT_U8, uint8_t, CARENV_FLAG_F32, float)
+    MCASE(CARENV_ACT_I32, int32_t, CARENV_FLAG_U8, uint8_t)
+    MCASE(CARENV_ACT_I32, int32_t, CARENV_FLAG_F32, float)
+    MCASE(CARENV_ACT_I64, int64_t, CARENV_FLAG_U8, uint8_t)
+    MCASE(CARENV_ACT_I64, int64_t, CARENV_FLAG_F32, float)
+#undef MCASE
+    return fail(CARENV_E_INVAL, "unknown action_dtype / flag_dtype");
+}
+
+/* ---- headless rgb_array frames ---- */
+int carenv_render(void *handle, int n_outer_segments, int n_frames, const int32_t *env_index, const double *pos,
+                  const int32_t *ints, const float *obs, int width, int height, unsigned char *rgb_out, void *stream) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(CARENV_E_INVAL, "null handle");
+    if (n_frames < 0 || n_frames > 65535) return fail(CARENV_E_INVAL, "n_frames must be in 0..65535");
+    if (n_frames == 0) return 0;
+    if (width < 1 || height < 1 || (long long)width * height > (1LL << 26)) return fail(CARENV_E_INVAL, "bad frame size");
+    if (!env_index || !pos || !ints || !obs || !rgb_out) return fail(CARENV_E_INVAL, "null pointer");
+    if (n_outer_segments < 0 || n_outer_segments > h->host.P.n_seg) return fail(CARENV_E_INVAL, "bad n_outer_segments");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    const dim3 grid((unsigned)((width * height + 255) / 256), (unsigned)n_frames);
+    k_render<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->host.P, h->dev, n_outer_segments, n_frames, env_index, reinterpret_cast<const double2 *>(pos),
+        reinterpret_cast<const int4 *>(ints), obs, width, height, rgb_out);
+    CU(cudaGetLastError());
+    return 0;
 }
 
 int carenv_set_option(void *handle, const char *name, int value) {

@@ -26,6 +26,7 @@ class Track:
     start: tuple           # (x, y) pixels
     angle: float           # degrees
     path: str
+    n_outer: int = 0       # how many of the wall segments belong to the outer polyline (rendering)
 
 
 def builtin_track(name: str) -> str:
@@ -51,7 +52,8 @@ def load_track(path: str) -> Track:
     walls = np.concatenate([np.hstack([outer[:-1], outer[1:]]), np.hstack([inner[:-1], inner[1:]])])
     gates = np.hstack([gpts[0:2 * n_g:2], gpts[1:2 * n_g:2]])
     start = (raw["initial_position"][0] * WIDTH, raw["initial_position"][1] * HEIGHT)
-    return Track(np.ascontiguousarray(walls), np.ascontiguousarray(gates), start, float(raw["initial_angle"]), path)
+    return Track(np.ascontiguousarray(walls), np.ascontiguousarray(gates), start, float(raw["initial_angle"]), path,
+                 len(outer) - 1)
 
 
 def _point_in_polygon(pt, poly) -> bool:

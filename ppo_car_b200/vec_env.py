@@ -62,10 +62,12 @@ def _ptr(t):
 class VecCarEnv:
     def __init__(self, n_envs: int, track_path: str | None = None, device="cuda", reward_scaling: float = 1.0,
                  float_flags: bool = False, with_info: bool = True, _out: dict | None = None,
-                 copy_outputs: bool = False, debug_info: bool = False):
+                 copy_outputs: bool = False, debug_info: bool = False, final_observation: bool = False):
         """``copy_outputs=True``: step / reset return fresh copies (the reference's semantics) instead of views of the
         internal buffers.  ``debug_info=True``: the numpy step also returns ``next_gate_index`` and ``events`` (16 more
-        bytes per environment over PCIe; the parity tests use them)."""
+        bytes per environment over PCIe; the parity tests use them).  ``final_observation=True``: step() with CUDA actions
+        also returns ``info["final_observation"]`` [N, 18] — the observation each step ended in BEFORE the autoreset — and
+        the mask ``info["_final_observation"]`` (gymnasium's vector-env convention)."""
         if n_envs < 1:
             raise ValueError("n_envs must be >= 1")
         self._L = _lib.lib()                       # raises if the CUDA extension is missing
@@ -82,6 +84,8 @@ class VecCarEnv:
         self.with_info = bool(with_info)
         self.copy_outputs = bool(copy_outputs)
         self.debug_info = bool(debug_info)
+        self.final_observation = bool(final_observation)
+        self._fobs = None
         low = np.array([0, 0, -1, -1, -1, -1] + [0] * 12, np.float32)
         high = np.ones(OBS_DIM, np.float32)
         self.single_observation_space = Box(low, high)
@@ -174,19 +178,31 @@ class VecCarEnv:
             raise ValueError(f"expected {self.num_envs} actions, got {actions.numel()}")
         if not actions.is_contiguous():
             actions = actions.contiguous()
+        flag_code = _lib.FLAG_F32 if self.float_flags else _lib.FLAG_U8
         with torch.cuda.device(self.device):
-            rc = self._L.carenv_step(self._handle, self.num_envs, _ptr(self.pos), _ptr(self.vel), _ptr(self.ints),
-                                     _ptr(actions), _ACT_CODES[actions.dtype], self.reward_scaling, _ptr(self._obs),
-                                     _ptr(self._rew), _ptr(self._term), _ptr(self._trunc),
-                                     _lib.FLAG_F32 if self.float_flags else _lib.FLAG_U8, _ptr(self._info),
-                                     self._stream())
+            if self.final_observation:
+                if self._fobs is None:
+                    self._fobs = torch.empty((self.num_envs, OBS_DIM), dtype=torch.float32, device=self.device)
+                rc = self._L.carenv_step_final(self._handle, self.num_envs, _ptr(self.pos), _ptr(self.vel),
+                                               _ptr(self.ints), _ptr(actions), _ACT_CODES[actions.dtype],
+                                               self.reward_scaling, _ptr(self._obs), _ptr(self._fobs), _ptr(self._rew),
+                                               _ptr(self._term), _ptr(self._trunc), flag_code, _ptr(self._info),
+                                               self._stream())
+            else:
+                rc = self._L.carenv_step(self._handle, self.num_envs, _ptr(self.pos), _ptr(self.vel), _ptr(self.ints),
+                                         _ptr(actions), _ACT_CODES[actions.dtype], self.reward_scaling, _ptr(self._obs),
+                                         _ptr(self._rew), _ptr(self._term), _ptr(self._trunc), flag_code,
+                                         _ptr(self._info), self._stream())
         _lib.check(rc, "carenv_step")
         term = self._term if self.float_flags else self._term.view(torch.bool)
         trunc = self._trunc if self.float_flags else self._trunc.view(torch.bool)
+        info = self._info_dict(self._info.clone() if (self.copy_outputs and self._info is not None) else self._info)
+        if self.final_observation:
+            info["final_observation"] = self._fobs.clone() if self.copy_outputs else self._fobs
+            info["_final_observation"] = (self._term != 0) | (self._trunc != 0)
         if self.copy_outputs:
-            info = None if self._info is None else self._info.clone()
-            return self._obs.clone(), self._rew.clone(), term.clone(), trunc.clone(), self._info_dict(info)
-        return self._obs, self._rew, term, trunc, self._info_dict(self._info)
+            return self._obs.clone(), self._rew.clone(), term.clone(), trunc.clone(), info
+        return self._obs, self._rew, term, trunc, info
 
     _REC_DTYPE = np.dtype([("reward", "<f8"), ("gates_passed", "<i4"), ("time_passed", "<u2"),
                            ("terminated", "?"), ("truncated", "?")])              # carenv_step_record, 16 bytes
@@ -313,6 +329,25 @@ class VecCarEnv:
         _lib.check(rc, "carenv_observe")
         return out
 
+    def render(self, env_indices=(0,), width: int = 1280, height: int = 720) -> torch.Tensor:
+        """Headless ``render_mode="rgb_array"`` frames (lib/car_env.py:762-812) of a few environments in their CURRENT
+        state: uint8 CUDA tensor [k, height, width, 3].  ``.cpu().numpy()`` is what train.py:23-50 (log_video) feeds
+        to cv2.  The picture shows background, corridor, walls, active gates (next one yellow), rays and the car as a
+        box; it is a diagnostic rendering, not pygame's rasteriser."""
+        if self._needs_reset:
+            raise _lib.CarEnvError("call reset() before render()")
+        idx = torch.as_tensor(list(env_indices), dtype=torch.int32, device=self.device).reshape(-1)
+        if idx.numel() == 0 or int(idx.min()) < 0 or int(idx.max()) >= self.num_envs:
+            raise ValueError("env_indices must name existing environments")
+        if (width, height) != (1280, 720):
+            raise ValueError("the canvas is the reference's 1280 x 720 (track coordinates are pixels of that canvas)")
+        out = torch.empty((idx.numel(), height, width, 3), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._L.carenv_render(self._handle, self.track.n_outer, idx.numel(), _ptr(idx), _ptr(self.pos),
+                                       _ptr(self.ints), _ptr(self._obs), width, height, _ptr(out), self._stream())
+        _lib.check(rc, "carenv_render")
+        return out
+
     def set_option(self, name: str, value: int) -> None:
         _lib.check(self._L.carenv_set_option(self._handle, name.encode(), int(value)), "carenv_set_option")
 
@@ -335,65 +370,119 @@ class VecCarEnv:
 
 
 class MultiTrackVecEnv:
-    """Several tracks in one vector env: environments [lo_i, hi_i) run on track i.  Every group is
-    a VecCarEnv with its own handle (per-track tables) writing straight into its slice of the shared output
-    tensors, so ``step`` returns the same 5-tuple as VecCarEnv over all environments; the groups' kernels are
-    launched back to back on the caller's stream."""
+    """Several tracks in one vector env (the reference selects a track per env with
+    ``reset(options={"track_path": ...})``, lib/car_env.py:621-628).  Every environment carries a track id and ALL of
+    them are stepped by ONE kernel launch (carenv_multi_rollout); environments of different tracks may be mixed in
+    any order.  Rows are bit-identical to a single-track VecCarEnv stepped with the same actions.
 
-    def __init__(self, groups, device="cuda", reward_scaling: float = 1.0, float_flags: bool = False):
-        """groups: list of (track_path, n_envs)."""
-        if not groups:
-            raise ValueError("need at least one (track_path, n_envs) group")
+        MultiTrackVecEnv([(path_a, 300), (path_b, 500)])                 # contiguous groups
+        MultiTrackVecEnv(track_paths=[path_a, path_b], track_ids=ids)     # ids: [N] ints, any assignment
+    """
+
+    def __init__(self, groups=None, device="cuda", reward_scaling: float = 1.0, float_flags: bool = False,
+                 track_paths=None, track_ids=None):
+        self._L = _lib.lib()
+        if not torch.cuda.is_available():
+            raise _lib.CarEnvError("MultiTrackVecEnv needs a CUDA device (there is no CPU implementation)")
         self.device = torch.device(device)
-        if self.device.type == "cuda" and self.device.index is None and torch.cuda.is_available():
+        if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self.num_envs = sum(int(n) for _, n in groups)
+        if groups is not None:
+            if not groups:
+                raise ValueError("need at least one (track_path, n_envs) group")
+            track_paths = [p for p, _ in groups]
+            track_ids = np.concatenate([np.full(int(c), i, np.int32) for i, (_, c) in enumerate(groups)])
+        if track_paths is None or track_ids is None:
+            raise ValueError("pass groups=[(track_path, n_envs), ...] or track_paths=[...] and track_ids=[...]")
+        self.reward_scaling, self.float_flags = float(reward_scaling), bool(float_flags)
+        self._multi = None
+        self._tracks: list[VecCarEnv] = []
+        self._set_tracks(list(track_paths))
+        ids = torch.as_tensor(np.asarray(track_ids), dtype=torch.int32).reshape(-1)
+        self.num_envs = int(ids.numel())
+        self._set_ids(ids)
         n, dev = self.num_envs, self.device
         fdt = torch.float32 if float_flags else torch.uint8
+        self.pos = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+        self.vel = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+        self.ints = torch.zeros((n, 4), dtype=torch.int32, device=dev)
         self._obs = torch.empty((n, OBS_DIM), dtype=torch.float32, device=dev)
         self._rew = torch.empty((n,), dtype=torch.float32, device=dev)
         self._term = torch.empty((n,), dtype=fdt, device=dev)
         self._trunc = torch.empty((n,), dtype=fdt, device=dev)
         self._info = torch.empty((n, 4), dtype=torch.int32, device=dev)
-        self.float_flags = bool(float_flags)
-        self.envs, self.ranges, lo = [], [], 0
-        for path, cnt in groups:
-            hi = lo + int(cnt)
-            out = dict(obs=self._obs[lo:hi], rew=self._rew[lo:hi], term=self._term[lo:hi], trunc=self._trunc[lo:hi],
-                       info=self._info[lo:hi])
-            self.envs.append(VecCarEnv(int(cnt), path, device=dev, reward_scaling=reward_scaling,
-                                       float_flags=float_flags, with_info=True, _out=out))
-            self.ranges.append((lo, hi))
-            lo = hi
-        self.single_observation_space = self.envs[0].single_observation_space
-        self.single_action_space = self.envs[0].single_action_space
+        self.single_observation_space = self._tracks[0].single_observation_space
+        self.single_action_space = self._tracks[0].single_action_space
+        self._needs_reset = True
+
+    def _set_tracks(self, paths):
+        """One single-track handle per path (they own the tables), then the multi-track handle over them."""
+        tracks = [VecCarEnv(1, p, device=self.device) for p in paths]
+        arr = (C.c_void_p * len(tracks))(*[t._handle for t in tracks])
+        multi = C.c_void_p()
+        _lib.check(self._L.carenv_multi_create(arr, len(tracks), C.byref(multi)), "carenv_multi_create")
+        if self._multi is not None:
+            self._L.carenv_multi_destroy(self._multi)
+            for t in self._tracks:
+                t.close()
+        self._multi, self._tracks, self.track_paths = multi, tracks, list(paths)
+        self._needs_reset = True
+
+    def _set_ids(self, ids):
+        ids = torch.as_tensor(np.asarray(ids.cpu() if isinstance(ids, torch.Tensor) else ids), dtype=torch.int32).reshape(-1)
+        if ids.numel() != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} track ids, got {ids.numel()}")
+        if int(ids.min()) < 0 or int(ids.max()) >= len(self._tracks):
+            raise ValueError(f"track ids must be in 0..{len(self._tracks) - 1}")
+        self.track_ids = ids.to(self.device)
+        self._needs_reset = True
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def reset(self, seed=None, options=None):
-        """``options={"track_paths": [path_0, path_1, ...]}`` switches every group to a new track (one path per
-        group, CarEnv.reset(options={"track_path": ...}) per group, lib/car_env.py:621-628); any other option is
-        refused rather than silently ignored."""
-        paths = None
+        """``options={"track_paths": [...]}`` replaces the track list (lib/car_env.py:621-628 for every env),
+        ``options={"track_ids": [N ints]}`` re-assigns environments to tracks; both may be given.  Any other option
+        is refused rather than silently ignored.  ``seed`` is accepted and ignored like in the reference."""
         if options:
-            unknown = set(options) - {"track_paths"}
+            unknown = set(options) - {"track_paths", "track_ids"}
             if unknown:
                 raise ValueError(f"MultiTrackVecEnv.reset does not understand options {sorted(unknown)}; "
-                                 "use options={'track_paths': [one path per group]}")
-            paths = list(options["track_paths"])
-            if len(paths) != len(self.envs):
-                raise ValueError(f"expected {len(self.envs)} track paths, got {len(paths)}")
-        for i, env in enumerate(self.envs):
-            env.reset(seed=seed, options={"track_path": paths[i]} if paths else None)
+                                 "use 'track_paths' (one path per track) and / or 'track_ids' (one id per env)")
+            if "track_paths" in options:
+                paths = list(options["track_paths"])
+                if "track_ids" not in options and len(paths) != len(self._tracks):
+                    raise ValueError(f"expected {len(self._tracks)} track paths (or pass new track_ids too), got {len(paths)}")
+                self._set_tracks(paths)
+            if "track_ids" in options:
+                self._set_ids(options["track_ids"])
+        with torch.cuda.device(self.device):
+            rc = self._L.carenv_multi_reset(self._multi, self.num_envs, _ptr(self.track_ids), _ptr(self.pos),
+                                            _ptr(self.vel), _ptr(self.ints), _ptr(self._obs), self._stream())
+        _lib.check(rc, "carenv_multi_reset")
+        self._needs_reset = False
         zeros = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         return self._obs, {"gates_passed": zeros, "time_passed": zeros.clone()}
 
-    def step(self, actions: torch.Tensor):
+    def step(self, actions):
+        """One step of every environment, all tracks in one launch.  Returns views of internal buffers that the next
+        step overwrites (see VecCarEnv)."""
+        if self._needs_reset:
+            raise _lib.CarEnvError("call reset() before step()")
         if not (isinstance(actions, torch.Tensor) and actions.is_cuda):
             actions = torch.as_tensor(np.asarray(actions), device=self.device)
-        actions = actions.reshape(-1)
+        if actions.dtype not in _ACT_CODES:
+            actions = actions.to(torch.int64)
+        actions = actions.reshape(-1).contiguous()
         if actions.numel() != self.num_envs:
             raise ValueError(f"expected {self.num_envs} actions, got {actions.numel()}")
-        for env, (lo, hi) in zip(self.envs, self.ranges):
-            env._step_device(actions[lo:hi])
+        with torch.cuda.device(self.device):
+            rc = self._L.carenv_multi_rollout(self._multi, self.num_envs, 1, _ptr(self.track_ids), _ptr(self.pos),
+                                              _ptr(self.vel), _ptr(self.ints), _ptr(actions), _ACT_CODES[actions.dtype],
+                                              self.reward_scaling, _ptr(self._obs), _ptr(self._rew), _ptr(self._term),
+                                              _ptr(self._trunc), _lib.FLAG_F32 if self.float_flags else _lib.FLAG_U8,
+                                              _ptr(self._info), self._stream())
+        _lib.check(rc, "carenv_multi_rollout")
         term = self._term if self.float_flags else self._term.view(torch.bool)
         trunc = self._trunc if self.float_flags else self._trunc.view(torch.bool)
         info = {"gates_passed": self._info[:, 0], "time_passed": self._info[:, 1], "next_gate_index": self._info[:, 2],
@@ -401,5 +490,15 @@ class MultiTrackVecEnv:
         return self._obs, self._rew, term, trunc, info
 
     def close(self):
-        for env in self.envs:
-            env.close()
+        if self._multi is not None:
+            self._L.carenv_multi_destroy(self._multi)
+            self._multi = None
+        for t in self._tracks:
+            t.close()
+        self._tracks = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -374,9 +374,14 @@ def test_adversarial_poses_on_gpu(tracks_dir):
     assert counts["line"] + counts["band"] > 500 and 0 < alive.sum() < n
 
 
-def test_multi_track_vector_env(tracks_dir):
-    """Two tracks in one vector env: each group's rows equal a single-track VecCarEnv stepped with the same actions."""
+def test_multi_track_vector_env(tracks_dir, tmp_path):
+    """Three tracks in one vector env, ONE launch per step (carenv_multi_rollout): contiguous groups and a random
+    per-env assignment — every env's rows equal a single-track VecCarEnv stepped with the same actions, bit for bit;
+    reset(options=...) re-assigns environments and swaps the track list."""
+    from tests.synth_tracks import ring_track
+
     pa, pb = os.path.join(tracks_dir, "track.json"), os.path.join(tracks_dir, "big_track.json")
+    pc = ring_track(str(tmp_path / "ring.json"), 10, 6)
     multi = ppo_car_b200.MultiTrackVecEnv([(pa, 300), (pb, 500)], reward_scaling=0.1)
     ea, eb = ppo_car_b200.VecCarEnv(300, pa, reward_scaling=0.1), ppo_car_b200.VecCarEnv(500, pb, reward_scaling=0.1)
     obs, _ = multi.reset()
@@ -393,7 +398,93 @@ def test_multi_track_vector_env(tracks_dir):
         assert torch.equal(r[:300], r1) and torch.equal(r[300:], r2)
         assert torch.equal(te[:300], te1) and torch.equal(te[300:], te2)
         assert torch.equal(info["gates_passed"][300:], i2["gates_passed"])
+    assert torch.equal(multi.pos[:300], ea.pos) and torch.equal(multi.ints[300:], eb.ints)
+    with pytest.raises(ValueError):
+        multi.reset(options={"track_path": pa})                 # unknown option: refused, not ignored
+    # arbitrary per-env assignment over three tracks (environments of different tracks share warps)
+    n = 1500
+    ids = np.random.default_rng(2).integers(0, 3, size=n).astype(np.int32)
     multi.close()
+    multi = ppo_car_b200.MultiTrackVecEnv(track_paths=[pa, pb, pc], track_ids=ids)
+    singles = [ppo_car_b200.VecCarEnv(int((ids == k).sum()), p) for k, p in enumerate((pa, pb, pc))]
+    obs, _ = multi.reset()
+    for k, e in enumerate(singles):
+        o0, _ = e.reset()
+        assert torch.equal(obs[torch.from_numpy(ids == k).cuda()], o0)
+    for _ in range(150):
+        a = torch.randint(0, 9, (n,), generator=g, device="cuda")
+        o, r, te, tr, info = multi.step(a)
+        for k, e in enumerate(singles):
+            m = torch.from_numpy(ids == k).cuda()
+            ok, rk, tek, trk, ik = e.step(a[m])
+            assert torch.equal(o[m], ok) and torch.equal(r[m], rk) and torch.equal(te[m], tek) and torch.equal(tr[m], trk)
+            assert torch.equal(info["time_passed"][m], ik["time_passed"])
+    assert int(te.sum()) >= 0 and int(multi.ints[:, 3].max()) > 0
+    # reset(options): new assignment, then a new track list
+    ids2 = (ids + 1) % 3
+    obs, _ = multi.reset(options={"track_ids": ids2})
+    assert torch.equal(obs[torch.from_numpy(ids2 == 0).cuda()][0], singles[0].reset()[0][0])
+    obs, _ = multi.reset(options={"track_paths": [pb, pa], "track_ids": np.zeros(n, np.int32)})
+    assert torch.equal(obs[0], singles[1].reset()[0][0])
+    multi.close()
+
+
+def test_final_observation_output(tracks_dir):
+    """gymnasium's info["final_observation"]: the observation each step ended in BEFORE the autoreset.  Equal to obs
+    where the episode goes on; where it ended it must equal the oracle's pre-reset observation."""
+    path = os.path.join(tracks_dir, "big_track.json")
+    for n in (48, 5000):                                          # warp-per-env kernel and thread-per-env kernel
+        T = 120
+        acts = np.random.default_rng(n).choice(9, size=(T, n), p=[.5, .02, .05, .05, .15, .15, .02, .02, .04]).astype(np.uint8)
+        ora = COracleVecEnv(n, path, scan_all_gates=False)
+        ora.reset()
+        ref = ora.rollout(acts, want=("obs", "fobs", "term", "trunc"))
+        env = ppo_car_b200.VecCarEnv(n, path, final_observation=True)
+        plain = ppo_car_b200.VecCarEnv(n, path)
+        env.reset()
+        plain.reset()
+        n_done = 0
+        for t in range(T):
+            a = torch.from_numpy(acts[t]).cuda()
+            o, r, te, tr, info = env.step(a)
+            o2, r2, te2, tr2, _ = plain.step(a)
+            assert torch.equal(o, o2) and torch.equal(r, r2) and torch.equal(te, te2)
+            done = (te | tr)
+            assert torch.equal(info["_final_observation"], done)
+            f = info["final_observation"]
+            assert torch.equal(f[~done], o[~done])
+            assert_floats_close(f.cpu().numpy(), ref["fobs"][t], f"final observation, step {t}")
+            n_done += int(done.sum())
+        assert n_done > n // 4
+
+
+def test_render_rgb_array_frames(tracks_dir):
+    """Headless rgb_array frames (lib/car_env.py:762-812): shape / dtype and the colours at known places."""
+    path = os.path.join(tracks_dir, "big_track.json")
+    env = ppo_car_b200.VecCarEnv(16, path)
+    env.reset()
+    for _ in range(10):
+        env.step(torch.zeros(16, dtype=torch.int64, device="cuda"))
+    frames = env.render(env_indices=[0, 5])
+    assert frames.shape == (2, 720, 1280, 3) and frames.dtype == torch.uint8
+    f = frames[0].cpu().numpy()
+    assert torch.equal(frames[0], frames[1])                       # same actions, same state
+    assert tuple(f[2, 2]) == (11, 102, 35)                         # outside the outer polygon: background
+    tr = env.track
+    cx, cy = (int(round(v)) for v in env.pos[0].cpu().numpy())
+    assert tuple(f[cy, cx]) in ((200, 30, 30), (250, 220, 60))     # the car
+    wx, wy = (tr.walls[0, :2] + tr.walls[0, 2:]) / 2               # middle of the first wall segment: black
+    assert tuple(f[int(wy), int(wx)]) == (0, 0, 0)
+    nxt = int(env.ints[0, 2])
+    gx, gy = (tr.gates[nxt, :2] * 0.5 + tr.gates[nxt, 2:] * 0.5)
+    assert tuple(f[int(gy), int(gx)]) in ((255, 255, 0), (255, 255, 255), (200, 30, 30), (250, 220, 60))   # next gate: yellow
+    later = min(nxt + 5, len(tr.gates) - 1)
+    gx, gy = (tr.gates[later, :2] * 0.5 + tr.gates[later, 2:] * 0.5)
+    assert tuple(f[int(gy), int(gx)]) in ((0, 255, 0), (255, 255, 255))                                     # later gates: green
+    start = tr.start
+    assert (f == np.array([190, 190, 190], np.uint8)).all(-1).sum() > 20_000                                # the corridor
+    with pytest.raises(ValueError):
+        env.render(env_indices=[99])
 
 
 @pytest.mark.parametrize("name,n_envs", [("big_track", 4099), ("track", 1500), ("ring 90+80", 700), ("ring 7+5", 300)])

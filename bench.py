@@ -370,7 +370,7 @@ def run_ours(args):
     for i in range(args.warmup):
         one_step(i)
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, period=args.clock_period)
     sampler.start()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -528,6 +528,7 @@ def run_ours(args):
                          "frac": achieved_tflops / fp32_nominal, "traffic": traffic,
                          "traffic_note": traffic_note + f"; algorithmic bytes per launch = {bytes_per_launch}",
                          "kernel": "k_rollout_tab<uint8,uint8,6>", "launch_ms": launch_ms,
+                         "launch_ms_min": min(per_launch_ms) / launches, "launch_ms_max": max(per_launch_ms) / launches,
                          "flop_per_env_step": FLOP_PER_ENV_STEP,
                          "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no "
                                         "FP32 entry)",
@@ -568,6 +569,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=256, help="env steps per rollout launch")
     ap.add_argument("--launches", type=int, default=1, help="rollout launches per timed bench step")
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--clock-period", type=float, default=0.01, help="seconds between NVML clock samples")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 2 / 3 / 5")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -501,8 +501,9 @@ def run_ours(args):
                 traffic_note = "profiles/r2_traffic.json was captured from other kernel sources: refused"
         except Exception:
             pass
-        configs = other_configs(dev, world) if not args.no_configs else None
-        cpu = cpu_baseline() if not args.no_cpu else None
+        # single-GPU side measurements: at N = 1 only (rank 0 would keep the other ranks waiting)
+        configs = other_configs(dev, world) if (world == 1 and not args.no_configs) else None
+        cpu = cpu_baseline() if (world == 1 and not args.no_cpu) else None
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,

@@ -1404,8 +1404,17 @@ static int step_host_impl(void *handle, int n_envs, double *pos, double *vel, in
     if (n_ranges > n_envs) n_ranges = n_envs;
     cudaStream_t user = static_cast<cudaStream_t>(stream);
     CU(cudaEventRecord(S.ready, user));                       // earlier work on the caller's stream (reset, device steps)
-    int lo_of[HostStep::kMaxRanges + 1];
-    for (int r = 0; r <= n_ranges; ++r) lo_of[r] = (int)((long long)n_envs * r / n_ranges);
+    // With four or more ranges the first one is split 1 : 3 (one more range): the device->host copies — the
+    // bottleneck — then start after a quarter-size narrowing + H2D + kernel instead of a full-size one.
+    int lo_of[HostStep::kMaxRanges + 2];
+    if (n_ranges >= 4 && h->host_ranges == 0) {
+        const int first = (int)((long long)n_envs / n_ranges);
+        lo_of[0] = 0; lo_of[1] = first / 4;
+        for (int r = 1; r <= n_ranges; ++r) lo_of[r + 1] = (int)((long long)n_envs * r / n_ranges);
+        n_ranges += 1;
+    } else {
+        for (int r = 0; r <= n_ranges; ++r) lo_of[r] = (int)((long long)n_envs * r / n_ranges);
+    }
     for (int r = 0; r < n_ranges; ++r) {
         const int lo = lo_of[r], m = lo_of[r + 1] - lo;
         if (action_dtype == CARENV_ACT_I64) {

@@ -3,9 +3,9 @@
     python oracle/make_ref.py            # needs /root/reference (the build container)
 
 The reference is pure Python (no build step), so "building" it is a byte-for-byte copy of the few
-files the hot path lives in, from where they lie under ``/root/reference`` into ``oracle/_ref/``:
+files the hot path and its caller's network live in, from where they lie under ``/root/reference`` into ``oracle/_ref/``:
 
-    lib/car_env.py   lib/buffer.py   tracks/track.json   tracks/big_track.json
+    lib/car_env.py   lib/buffer.py   lib/model.py   tracks/track.json   tracks/big_track.json
 
 ``oracle/_ref/`` is git-ignored (reference sources never enter this repository's history) but not
 gpurun-ignored, so the directory travels to the GPU box exactly like the built ``*.so`` files do.
@@ -28,7 +28,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("PPO_CAR_REFERENCE", "/root/reference")
 DST = os.path.join(HERE, "_ref")
-FILES = ["lib/car_env.py", "lib/buffer.py", "tracks/track.json", "tracks/big_track.json"]
+FILES = ["lib/car_env.py", "lib/buffer.py", "lib/model.py", "tracks/track.json", "tracks/big_track.json"]
 
 
 def sha256(path: str) -> str:

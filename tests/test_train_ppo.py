@@ -57,3 +57,31 @@ def test_graph_update_trains():
     assert all(math.isfinite(h["total_loss"]) for h in hist)
     assert hist[-1]["avg_reward"] > hist[0]["avg_reward"] + 0.03
     assert abs(hist[-1]["lr"] - 3e-4 * 0.99 ** 12) < 1e-9
+
+
+def test_state_dict_loads_into_the_reference_agent():
+    """The checkpoints train_ppo writes (train.py:280-283, 301) carry the reference Agent's keys: a state dict of
+    this harness's network loads strictly into the UNMODIFIED lib/model.py:Agent and both compute the same outputs."""
+    import importlib
+    import sys
+
+    from oracle.ref_import import reference_root
+
+    root = reference_root()
+    if root is None:
+        pytest.skip("neither /root/reference nor oracle/_ref is present")
+    import os
+
+    if not os.path.isfile(os.path.join(root, "lib", "model.py")):
+        pytest.skip("lib/model.py not in the reference copy (re-run oracle/make_ref.py)")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    Agent = importlib.import_module("lib.model").Agent
+    torch.manual_seed(3)
+    ours, ref = ActorCritic(18, 9), Agent(18, 9)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    obs = torch.randn(32, 18)
+    act, logp, ent, val = ours.act(obs)
+    a2, logp2, ent2, val2 = ref.get_action_and_value(obs, act)
+    assert torch.equal(a2, act) and torch.allclose(logp, logp2, atol=1e-6) and torch.allclose(ent, ent2, atol=1e-6)
+    assert torch.allclose(val, val2, atol=1e-6)

@@ -295,6 +295,7 @@ CE_HD void integrate(EnvState &s, int thrust, int k_pre, const Tables &T) {
 // ---- the 12 ray distances and the wall-collision decision -------------------------------------
 struct WallAcc {
     float c[3], sn[3];      // 2^50 * directions of lines 0..2 (heading + 0/30/60 deg); lines 3..5 are these rotated by 90 deg
+    double cd[3], sd[3];    // the same directions in float64, unscaled (denominators, seg_den)
     float cp[6];            // q' of the car's own position: q'(P) = cross(P, d') - cp  (see line_origin)
     float Rp[6], Rm[6];     // max of r = 1/u over hits with u > 0 (ray l) / min over hits with u < 0 (ray l+6)
     float gq[6];            // min |q'| per line  -> hit/miss guard
@@ -330,12 +331,14 @@ CE_HD void wall_chain_start(WallAcc &w, const SegF &f) {
     for (int l = 0; l < 6; ++l) w.gq[l] = fminf(w.gq[l], fabsf(w.qa[l]));
 }
 
-// The float32 denominators 2^50 cross(e, d) of one segment for one heading: (line l, line l + 3).  This is THE
-// definition — the kernels that take them from the per-track table (TabView) read values computed by this very
-// function on the host, so table and arithmetic paths agree bit for bit.
-CE_HD void seg_den(float ex, float ey, float sn, float c, float &den0, float &den3) {
-    den0 = ffma(ex, sn, -fmul(ey, c));
-    den3 = ffma(ex, c, fmul(ey, sn));
+// The denominators 2^50 cross(e, d) of one segment for one heading, (line l, line l + 3): evaluated in FLOAT64 from the
+// float64 segment vector and heading table and rounded once.  (In float32 the rounding of the heading's cos / sin
+// alone costs 6e-8 / sin(incidence) relative: 4e-5 for a ray that grazes a wall at 0.05 degrees — measured on
+// big_track, twice in 2e8 ray distances.)  This is THE definition: the table kernel reads values computed by this
+// very function on the host, the other kernels evaluate it on the FP64 pipe — same bits everywhere.
+CE_HD void seg_den(double exs, double eys, double sn, double c, float &den0, float &den3) {
+    den0 = (float)dfma(exs, sn, -dmul(eys, c));
+    den3 = (float)dfma(exs, c, dmul(eys, sn));
 }
 
 // One wall segment against the six lines.
@@ -351,10 +354,9 @@ CE_HD void wall_segment(WallAcc &w, const SegF &f, const SegD &g, double px, dou
     w.gu = fminf(w.gu, fabsf(un));
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
-        // cross(e, d_l) / cross(e, A') = 1/u.  (Pre-scaling e by inv would save a multiply per test but
-        // measurably costs accuracy: 1.2e-5 instead of 1.6e-6 worst relative distance error.)
+        // cross(e, d_l) / cross(e, A') = 1/u
         float den0, den3;
-        seg_den(f.ex, f.ey, w.sn[l], w.c[l], den0, den3);
+        seg_den(g.ex, g.ey, w.sd[l], w.cd[l], den0, den3);
         const float h0 = fmul(fmul(den0, inv), sat_mul(w.qa[l], -qb[l]));            // r * (hit ? 1 : 0)
         const float h3 = fmul(fmul(den3, inv), sat_mul(w.qa[l + 3], -qb[l + 3]));
         w.Rp[l] = fmaxf(w.Rp[l], h0); w.Rm[l] = fminf(w.Rm[l], h0);
@@ -376,6 +378,7 @@ CE_HD void wall_segment(WallAcc &w, const SegF &f, const SegD &g, double px, dou
 struct WallAcc2 {
     P2 S[3];                // S_l = 2^50 (s_l, c_l); its half-swap (c_l, s_l) is a free operand modifier
     P2 CP[3];               // (cp_l, cp_{l+3}): q' of the car's own position (line_origin2)
+    D2 T64[3];              // (cos, sin) of the three lines in float64 (denominators of the arithmetic path; unused with TAB)
     float Rp[6], Rm[6], gq[6], gu;
     P2 QA[3];               // (q'_l, q'_{l+3}) of the previous endpoint
 };
@@ -416,8 +419,8 @@ CE_HD void wall_chain_start2(WallAcc2 &w, const SegF &f) {
     }
 }
 
-// TAB: the denominators come from the table rows tb[l] (entry jp) instead of one FMUL2 + FFMA2 per segment and
-// line pair — same values (seg_den), 4 packed FMA-pipe instructions less per pair and line.
+// TAB: the denominators come from the table rows tb[l] (entry jp) instead of two DMUL + two DFMA + two F2F per segment
+// and line pair — same values (seg_den).
 template <bool TAB>
 CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1, const SegD &g1, double px,
                      double py, const float4 *const *tb = nullptr, int jp = 0) {
@@ -436,9 +439,10 @@ CE_HD void wall_pair(WallAcc2 &w, const SegF &f0, const SegD &g0, const SegF &f1
             const float4 t = tb[l][jp];
             D0 = p2(t.x, t.y); D1 = p2(t.z, t.w);
         } else {
-            const P2 SW = p2(w.S[l].y, w.S[l].x);
-            D0 = pfma(p2(h0.ex, h0.ex), w.S[l], pmul(p2(f0.ney, f0.ey), SW));
-            D1 = pfma(p2(h1.ex, h1.ex), w.S[l], pmul(p2(f1.ney, f1.ey), SW));
+            float a0, a3, b0, b3;
+            seg_den(g0.ex, g0.ey, w.T64[l].y, w.T64[l].x, a0, a3);
+            seg_den(g1.ex, g1.ey, w.T64[l].y, w.T64[l].x, b0, b3);
+            D0 = p2(a0, a3); D1 = p2(b0, b3);
         }
         const P2 R0 = pmul(D0, p2(inv0, inv0)), R1 = pmul(D1, p2(inv1, inv1));
         const P2 H0 = pmul(R0, p2(sat_mul(w.QA[l].x, -QB0[l].x), sat_mul(w.QA[l].y, -QB0[l].y)));
@@ -472,8 +476,10 @@ __device__ __forceinline__ void cast_walls_warp(const EnvState &s, const Tables 
     WallAcc w;
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
-        const F2 d = T.trig32s[wrap72(s.k + 6 * l)];
-        w.c[l] = d.x; w.sn[l] = d.y;
+        const int kl = wrap72(s.k + 6 * l);
+        const F2 d = T.trig32s[kl];
+        const D2 dd = T.trig64[kl];
+        w.c[l] = d.x; w.sn[l] = d.y; w.cd[l] = dd.x; w.sd[l] = dd.y;
     }
     line_origin(w, s.px, s.py);
     float qa[6], qb[6];
@@ -486,7 +492,7 @@ __device__ __forceinline__ void cast_walls_warp(const EnvState &s, const Tables 
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
         float den0, den3;
-        seg_den(ws.f.ex, ws.f.ey, w.sn[l], w.c[l], den0, den3);
+        seg_den(ws.g.ex, ws.g.ey, w.sd[l], w.cd[l], den0, den3);
         const float h0 = on ? fmul(fmul(den0, inv), sat_mul(qa[l], -qb[l])) : 0.0f;
         const float h3 = on ? fmul(fmul(den3, inv), sat_mul(qa[l + 3], -qb[l + 3])) : 0.0f;
         rp[l] = fmaxf(R0, h0);          rm[l] = fminf(-R0, h0);
@@ -533,6 +539,7 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
             w.S[l] = p2(d.y, d.x);
             w.QA[l] = p2(0.0f, 0.0f);
             if (TAB) tb[l] = tv->base + kl * tv->row_f4;
+            else w.T64[l] = T.trig64[kl];
         }
         line_origin2(w, s.px, s.py);
 #pragma unroll
@@ -553,8 +560,10 @@ CE_HD bool cast_walls(const EnvState &s, const TrackParams &P, const Tables &T, 
         WallAcc w;
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
-            const F2 d = T.trig32s[wrap72(s.k + 6 * l)];
-            w.c[l] = d.x; w.sn[l] = d.y;
+            const int kl = wrap72(s.k + 6 * l);
+            const F2 d = T.trig32s[kl];
+            const D2 dd = T.trig64[kl];
+            w.c[l] = d.x; w.sn[l] = d.y; w.cd[l] = dd.x; w.sd[l] = dd.y;
         }
         line_origin(w, s.px, s.py);
 #pragma unroll

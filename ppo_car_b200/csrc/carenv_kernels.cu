@@ -1154,10 +1154,10 @@ int launch_rollout(Handle *h, int n_envs, int n_steps, double *pos, double *vel,
     int U = h->force_generic ? 1 : h->host.P.unroll;
     if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
     if (h->host.P.n_seg > kMaxSeg) U = 0;                   // geometry from shared memory
-    // large launches: denominators from the shared-memory table (k_rollout_tab).  "Large" = at least two warps per
-    // scheduler on every SM and enough steps to amortise staging the table copies (147 KB per CTA on big_track).
-    if (U >= 2 && h->d_den4 && h->tab >= 0 && !h->cur_fobs &&
-        (h->tab == 1 || (n_envs >= 148 * 384 && (long long)n_envs * n_steps >= (1LL << 22)))) {
+    // 4,096 environments or more: denominators from the shared-memory table (k_rollout_tab) — measured equal or faster
+    // than k_rollout from there on for every launch length, single steps included (benchmarks/ab_step.py: 1 M envs x 1
+    // step 92 vs 120 us; the arithmetic kernels evaluate the denominators on the FP64 pipe).
+    if (U >= 2 && h->d_den4 && h->tab >= 0 && !h->cur_fobs && (h->tab == 1 || n_envs >= 4096)) {
         const int rc = launch_rollout_tab<ActT, FlagT>(h, U, n_envs, n_steps, pos, vel, ints, actions, reward_scale,
                                                        obs_out, reward_out, term_out, trunc_out, info_out, stream,
                                                        obs_mode);

@@ -83,7 +83,9 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
     // guard bands: bounds on the float32 error of q, r and the gate margin
     P.eps_q = 1.5e-3f;      // |dq| <= 5.7e-4 px for coordinates within 1280 x 720 (see wall_point)
     P.eps_qs = P.eps_q * kQScale;
-    const double rel_r = 4.0e-7 / min_sin + 3.0e-7;   // relative error of r = cross(e,d) / cross(e,A')
+    (void)min_sin;
+    const double rel_r = 5.0e-7;   // relative error of r = cross(e,d) / cross(e,A'): both from float64, rounded once, one
+                                   // approximate reciprocal, one multiply
     P.coll_band = (float)fmax(2.0e-4, 4.0 * rel_r);
     P.tiny_d = 1.0e-2f;
     P.gate_band = 2.0e-3f;
@@ -110,9 +112,9 @@ inline int build_host_track(const double *walls, int n_walls, const double *gate
         for (int k = 0; k < kHeadings; ++k)
             for (int jp = 0; jp < H.n_pairs; ++jp) {
                 float *d = &H.den4[((size_t)k * H.n_pairs + jp) * 4];
-                const F2 t = H.trig32s[k];
-                seg_den(H.segf[2 * jp].ex, H.segf[2 * jp].ey, t.y, t.x, d[0], d[1]);
-                seg_den(H.segf[2 * jp + 1].ex, H.segf[2 * jp + 1].ey, t.y, t.x, d[2], d[3]);
+                const D2 t = H.trig64[k];
+                seg_den(H.segd[2 * jp].ex, H.segd[2 * jp].ey, t.y, t.x, d[0], d[1]);
+                seg_den(H.segd[2 * jp + 1].ex, H.segd[2 * jp + 1].ey, t.y, t.x, d[2], d[3]);
             }
     }
 

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("CARENV_LIB") or os.path.join(_PKG, "libcarenv_b200.so")   # override: kernel experiments
 SOURCES = [os.path.join(_PKG, "csrc", f)
            for f in ("carenv_kernels.cu", "carenv_core.cuh", "carenv_tables.h", "policy_core.cuh", "tc_mlp.cuh",
-                     "ppo_update.cuh")]
+                     "ppo_update.cuh", "policy_rollout.cuh", "policy_abi.cuh")]
 HEADER = os.path.join(ROOT, "include", "carenv_b200.h")
 
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2

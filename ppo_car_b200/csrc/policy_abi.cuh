@@ -1,0 +1,163 @@
+// policy_abi.cuh — C-ABI entry points of the policy / PPO-update kernels (declared in include/carenv_b200.h).
+// Textually included by carenv_kernels.cu inside its extern "C" block.
+#pragma once
+int carenv_pack_policy(int tensor_cores, const float *w1a, const float *b1a, const float *w2a, const float *b2a,
+                       const float *w1c, const float *b1c, const float *w2c, const float *b2c, float *packed_out,
+                       void *stream) {
+    if (!w1a || !b1a || !w2a || !b2a || !w1c || !b1c || !w2c || !b2c || !packed_out)
+        return fail(CARENV_E_INVAL, "null pointer");
+    const int n = tensor_cores ? kTcWeightFloats : kPolicyFloats;
+    if (tensor_cores)
+        k_pack_policy<true><<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w1a, b1a, w2a, b2a, w1c, b1c,
+                                                                                           w2c, b2c, packed_out);
+    else
+        k_pack_policy<false><<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w1a, b1a, w2a, b2a, w1c, b1c,
+                                                                                            w2c, b2c, packed_out);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int carenv_ppo_num_params(void) { return ppo::kNumParams; }
+int carenv_ppo_scratch_floats(int batch) { return batch > 0 && batch <= ppo::kMaxBatch ? ppo::scratch_floats(batch) : -1; }
+
+int carenv_ppo_grad(const float *w1a, const float *b1a, const float *w2a, const float *b2a, const float *w1c,
+                    const float *b1c, const float *w2c, const float *b2c, const float *obs, int obs_is_gathered,
+                    const long long *idx, const float *act, const float *old_logp, const float *adv, const float *ret,
+                    int batch, double clip_ratio, double vf_coef, double ent_coef, float *scratch, float *grads,
+                    void *stream) {
+    if (batch < 2 || batch > ppo::kMaxBatch) return fail(CARENV_E_INVAL, "batch must be in 2..1024");
+    if (!w1a || !b1a || !w2a || !b2a || !w1c || !b1c || !w2c || !b2c || !obs || !idx || !act || !old_logp || !adv ||
+        !ret || !scratch || !grads)
+        return fail(CARENV_E_INVAL, "null pointer");
+    const ppo::Params P{w1a, b1a, w2a, b2a, w1c, b1c, w2c, b2c};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nb = (batch + ppo::kFwdThreads - 1) / ppo::kFwdThreads;
+    const size_t smem_f = sizeof(float) * (ppo::kH * 20 + ppo::kH * ppo::kDz + 4);
+    ppo::k_ppo_forward<<<dim3(nb, 2), ppo::kFwdThreads, smem_f, st>>>(P, obs, obs_is_gathered, idx, act, old_logp, adv,
+                                                                      ret, batch, (float)clip_ratio, (float)vf_coef,
+                                                                      (float)ent_coef, scratch);
+    CU(cudaGetLastError());
+    const size_t smem_b = sizeof(float) * ((size_t)batch * (20 + ppo::kDz) +
+                                           (size_t)ppo::kBwdSlices * ppo::kBwdUnits * (ppo::kIn + 1 + ppo::kQ + 1));
+    CU(cudaFuncSetAttribute(ppo::k_ppo_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    ppo::k_ppo_backward<<<dim3(ppo::kH / ppo::kBwdUnits, 2), ppo::kBwdUnits * ppo::kBwdSlices, smem_b, st>>>(P, batch,
+                                                                                                          scratch, grads);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int carenv_ppo_adam(float *w1a, float *b1a, float *w2a, float *b2a, float *w1c, float *b1c, float *w2c, float *b2c,
+                    float *grads, double grad_scale, float *exp_avg, float *exp_avg_sq, const float *lr, int *step,
+                    double beta1, double beta2, double eps, double max_grad_norm, const float *scratch, int batch,
+                    double vf_coef, double ent_coef, float *sums4, void *stream) {
+    if (batch < 2 || batch > ppo::kMaxBatch) return fail(CARENV_E_INVAL, "batch must be in 2..1024");
+    if (!w1a || !b1a || !w2a || !b2a || !w1c || !b1c || !w2c || !b2c || !grads || !exp_avg || !exp_avg_sq || !lr ||
+        !step || !scratch || !sums4)
+        return fail(CARENV_E_INVAL, "null pointer");
+    const ppo::MutableParams P{w1a, b1a, w2a, b2a, w1c, b1c, w2c, b2c};
+    ppo::k_ppo_adam<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+        P, grads, (float)grad_scale, exp_avg, exp_avg_sq, lr, step, (float)beta1, (float)beta2, (float)eps,
+        (float)max_grad_norm, scratch, batch, (float)vf_coef, (float)ent_coef, sums4);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int carenv_policy_weights_floats(void) { return kPolicyFloats; }
+
+int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs, int n_steps, int env_offset,
+                          unsigned long long seed, unsigned long long step0, double *pos, double *vel, int32_t *ints,
+                          float *cur_obs, float *cur_term, float *cur_trunc, double reward_scale, float *obs_buf,
+                          float *act_buf, float *rew_buf, float *val_buf, float *term_buf, float *trunc_buf,
+                          float *logp_buf, float *last_val, float *u_dbg, void *stream) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(CARENV_E_INVAL, "null handle");
+    if (n_envs < 0 || n_steps < 0) return fail(CARENV_E_INVAL, "negative n_envs / n_steps");
+    if (n_envs == 0) return 0;
+    if (!packed_weights || !pos || !vel || !ints || !cur_obs || !cur_term || !cur_trunc || !obs_buf || !act_buf ||
+        !rew_buf || !val_buf || !term_buf || !trunc_buf || !logp_buf)
+        return fail(CARENV_E_INVAL, "null pointer");
+    if (h->host.P.n_seg > kMaxSeg)
+        return fail(CARENV_E_TRACK, "the fused rollout kernels support tracks with at most 128 wall segments");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    const int table_bytes = (int)((h->smem_bytes + 15) / 16 * 16);
+    const size_t smem = (size_t)table_bytes + sizeof(float) * kPolicyFloats;
+    const int grid = (n_envs + kPolicyBlock - 1) / kPolicyBlock;
+    int U = h->force_generic ? 1 : h->host.P.unroll4;   // the fused kernels are instantiated for 4, 2, 1
+    if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
+    auto launch = [&](auto kern) -> int {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kPolicyBlock, smem, static_cast<cudaStream_t>(stream)>>>(
+            h->host.P, h->dev, packed_weights, n_envs, n_steps, env_offset, seed, step0,
+            reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints), cur_obs,
+            cur_term, cur_trunc, reward_scale, obs_buf, act_buf, rew_buf, val_buf, term_buf, trunc_buf, logp_buf,
+            last_val, u_dbg, h->d_stats, table_bytes, h->pose_rows ? kObsPose : kObsFull);
+        CU(cudaGetLastError());
+        return 0;
+    };
+    if (U == 4) return launch(k_policy_rollout<4>);
+    if (U == 2) return launch(k_policy_rollout<2>);
+    return launch(k_policy_rollout<1>);
+}
+
+/* Test hook: D[128,256] = A[128,24] * B[256,24]^T on the tensor cores (tcgen05, kind::tf32). */
+int carenv_tc_gemm_test(const float *A, const float *B, float *D, void *stream) {
+    if (!A || !B || !D) return fail(CARENV_E_INVAL, "null pointer");
+    const size_t smem = tc::kABytes + tc::kBBytes + 128;
+    CU(cudaFuncSetAttribute(k_tc_gemm_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tc_gemm_test<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, B, D);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int carenv_policy_weights_floats_tc(void) { return kTcWeightFloats; }
+
+/* Tensor-core variant of carenv_policy_rollout (same arguments; packed_weights in the layout of
+ * ppo_car_b200/policy.py: pack_policy_weights_tc). */
+int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_envs, int n_steps, int env_offset,
+                             unsigned long long seed, unsigned long long step0, double *pos, double *vel,
+                             int32_t *ints, float *cur_obs, float *cur_term, float *cur_trunc, double reward_scale,
+                             float *obs_buf, float *act_buf, float *rew_buf, float *val_buf, float *term_buf,
+                             float *trunc_buf, float *logp_buf, float *last_val, float *u_dbg, void *stream) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(CARENV_E_INVAL, "null handle");
+    if (n_envs < 0 || n_steps < 0) return fail(CARENV_E_INVAL, "negative n_envs / n_steps");
+    if (n_envs == 0) return 0;
+    if (!packed_weights || !pos || !vel || !ints || !cur_obs || !cur_term || !cur_trunc || !obs_buf || !act_buf ||
+        !rew_buf || !val_buf || !term_buf || !trunc_buf || !logp_buf)
+        return fail(CARENV_E_INVAL, "null pointer");
+    if (h->host.P.n_seg > kMaxSeg)
+        return fail(CARENV_E_TRACK, "the fused rollout kernels support tracks with at most 128 wall segments");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    const int table_bytes = (int)h->smem_bytes;
+    // groups per CTA: 2 while 4 would leave SMs without a CTA (one CTA per SM: the weights take 110 KB)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    int tiles = (n_envs + 511) / 512 >= sms ? 4 : 2;
+    if (h->tc_tiles == 2 || h->tc_tiles == 4) tiles = h->tc_tiles;
+    const size_t smem = (size_t)table_bytes + 128 + (size_t)((kTcWeightFloats * 4 + 127) / 128 * 128) +
+                        (size_t)tiles * 2 * tc::kABytes;
+    if (smem > 227 * 1024) return fail(CARENV_E_TRACK, "track tables too large for the tensor-core rollout kernel");
+    const int grid = (n_envs + tiles * 128 - 1) / (tiles * 128);
+    int U = h->force_generic ? 1 : h->host.P.unroll4;
+    if (h->max_unroll > 0 && U > h->max_unroll) U = (U % h->max_unroll == 0) ? h->max_unroll : 1;
+    auto launch = [&](auto kern) -> int {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, tiles * 128 + 32, smem, static_cast<cudaStream_t>(stream)>>>(
+            h->host.P, h->dev, packed_weights, n_envs, n_steps, env_offset, seed, step0,
+            reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints), cur_obs,
+            cur_term, cur_trunc, reward_scale, obs_buf, act_buf, rew_buf, val_buf, term_buf, trunc_buf, logp_buf,
+            last_val, u_dbg, h->d_stats, table_bytes, h->pose_rows ? kObsPose : kObsFull);
+        CU(cudaGetLastError());
+        return 0;
+    };
+    if (tiles == 4) {
+        if (U == 4) return launch(k_policy_rollout_tc<4, 4>);
+        if (U == 2) return launch(k_policy_rollout_tc<2, 4>);
+        return launch(k_policy_rollout_tc<1, 4>);
+    }
+    if (U == 4) return launch(k_policy_rollout_tc<4, 2>);
+    if (U == 2) return launch(k_policy_rollout_tc<2, 2>);
+    return launch(k_policy_rollout_tc<1, 2>);
+}

@@ -1,0 +1,434 @@
+// policy_rollout.cuh — the fused policy + environment rollout kernels and the tcgen05 bring-up test.
+// Textually included by carenv_kernels.cu inside its anonymous namespace (after the step kernels, whose helpers
+// stage_tables / store_pose / env_step it uses); kept in its own file so that the step path (carenv_core.cuh,
+// carenv_tables.h, carenv_kernels.cu) can be hashed on its own by bench.py / profiles/make_traffic.py.
+#pragma once
+// tcgen05 bring-up / unit test: D[128,256] = A[128,24] * B[256,24]^T with kind::tf32, accumulators in TMEM.
+__global__ void __launch_bounds__(128) k_tc_gemm_test(const float *__restrict__ A, const float *__restrict__ B,
+                                                      float *__restrict__ D) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned char *tsm = smem + ((128u - (tc::smem_u32(smem) & 127u)) & 127u);
+    unsigned char *sA = tsm, *sB = tsm + tc::kABytes;
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < tc::kTileM * tc::kK; i += blockDim.x)
+        *reinterpret_cast<float *>(sA + tc::operand_offset(i / tc::kK, i % tc::kK)) = A[i];
+    for (int i = tid; i < tc::kTileN * tc::kK; i += blockDim.x)
+        *reinterpret_cast<float *>(sB + tc::operand_offset(i / tc::kK, i % tc::kK)) = B[i];
+    if (tid == 0) tc::mbar_init(tc::smem_u32(&mbar), 1);
+    if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_tf32(128, 256);
+        for (int ks = 0; ks < tc::kK / 8; ++ks) {
+            const uint64_t da = tc::make_smem_desc(tc::smem_u32(sA) + ks * 2 * tc::kLBO);
+            const uint64_t db = tc::make_smem_desc(tc::smem_u32(sB) + ks * 2 * tc::kLBO);
+            tc::mma_tf32(tbase, da, db, idesc, ks > 0);
+        }
+        tc::mma_commit(tc::smem_u32(&mbar));
+    }
+    tc::mbar_wait(tc::smem_u32(&mbar), 0);
+    tc::tc_fence_after();
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < 256; c += 16) {
+        float v[16];
+        tc::tmem_ld16(lane_base + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) D[(size_t)tid * 256 + c + i] = v[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(tbase);
+}
+
+// Fused rollout: actor/critic forward, categorical sampling, CarEnv.step and the Buffer
+// row writes of train.py:173-195 for n_steps steps in ONE launch.  One thread per environment; the packed
+// policy weights (53 KB) and the per-thread-indexed track tables live in shared memory.
+#ifndef CARENV_POLICY_BLOCK
+#define CARENV_POLICY_BLOCK 128
+#endif
+#ifndef CARENV_POLICY_MIN_BLOCKS
+#define CARENV_POLICY_MIN_BLOCKS 3
+#endif
+constexpr int kPolicyBlock = CARENV_POLICY_BLOCK;
+template <int U>
+__global__ void __launch_bounds__(kPolicyBlock, CARENV_POLICY_MIN_BLOCKS)
+k_policy_rollout(const __grid_constant__ TrackParams P, const Tables G, const float *__restrict__ weights,
+                 int n_envs, int n_steps, int env_offset, unsigned long long seed, unsigned long long step0,
+                 double2 *__restrict__ pos, double2 *__restrict__ vel, int4 *__restrict__ ints,
+                 float *__restrict__ cur_obs, float *__restrict__ cur_term, float *__restrict__ cur_trunc,
+                 double reward_scale, float *__restrict__ obs_buf, float *__restrict__ act_buf,
+                 float *__restrict__ rew_buf, float *__restrict__ val_buf, float *__restrict__ term_buf,
+                 float *__restrict__ trunc_buf, float *__restrict__ logp_buf, float *__restrict__ last_val,
+                 float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes, int obs_mode) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *sw = reinterpret_cast<float *>(smem + table_bytes);
+    for (int i = threadIdx.x; i < kPolicyFloats / 4; i += blockDim.x)
+        reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(weights)[i];
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);      // ends with __syncthreads()
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+
+    EnvState s;
+    {
+        const double2 p = pos[e], v = vel[e];
+        const int4 q = ints[e];
+        s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
+        s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
+    }
+    float obs[kObsDim];
+    {
+        const float2 *src = reinterpret_cast<const float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+        for (int i = 0; i < kObsDim / 2; ++i) { const float2 v = src[i]; obs[2 * i] = v.x; obs[2 * i + 1] = v.y; }
+    }
+    float tc = cur_term[e], uc = cur_trunc[e];
+    const uint32_t gid = (uint32_t)(env_offset + e);
+    PolicyOut po;
+    for (int t = 0; t < n_steps; ++t) {
+        const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+        policy_forward(obs, sw, po);
+        const unsigned long long gs = step0 + (unsigned long long)t;
+        const uint32_t bits = philox_uniform_bits((uint32_t)seed, (uint32_t)(seed >> 32), gid, (uint32_t)gs,
+                                                  (uint32_t)(gs >> 32), 0x43415245u);
+        const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
+        float logp, us;
+        const int a = sample_action(po, u, logp, us);
+        if (obs_mode == kObsPose) {
+            store_pose(reinterpret_cast<PoseRec *>(obs_buf) + idx, s, obs[2], obs[3]);
+        } else {
+            float2 *dst = reinterpret_cast<float2 *>(obs_buf + idx * kObsDim);
+#pragma unroll
+            for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+        }
+        act_buf[idx] = (float)a;
+        val_buf[idx] = po.value;
+        logp_buf[idx] = logp;
+        term_buf[idx] = tc;
+        trunc_buf[idx] = uc;
+        if (u_dbg) u_dbg[idx] = u;
+        StepResult o;
+        env_step<U>(s, a, reward_scale, P, T, o, stats);
+        rew_buf[idx] = o.reward;
+#pragma unroll
+        for (int i = 0; i < kObsDim; ++i) obs[i] = o.obs[i];
+        tc = o.terminated ? 1.0f : 0.0f;
+        uc = o.truncated ? 1.0f : 0.0f;
+    }
+    pos[e] = make_double2(s.px, s.py);
+    vel[e] = make_double2(s.vx, s.vy);
+    ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+    {
+        float2 *dst = reinterpret_cast<float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+        for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+    }
+    cur_term[e] = tc;
+    cur_trunc[e] = uc;
+    if (last_val) {                                          // bootstrap value of the state after the rollout
+        policy_forward(obs, sw, po);
+        last_val[e] = po.value;
+    }
+}
+
+// ---- fused rollout, tensor-core version ---------------------------------------------------------------------
+// Same contract as k_policy_rollout, but the two 18->256 layers (23.6 of the 29 kflop per env-step) run on the
+// 5th-gen tensor cores: per step every thread writes its observation row (hi/lo TF32 split, a constant 1 in
+// column 18 carries the bias) into the K-major UMMA operand tile of its 128-env group, one elected thread issues
+// tcgen05.mma kind::tf32 for all kTcTiles groups — D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (3xTF32: float32-level
+// accuracy) — into tensor memory, and after the commit barrier every thread reads ITS row of pre-activations
+// back with tcgen05.ld, applies ReLU and the small second layer (FFMA2) and goes on to sampling and the env step.
+// TMEM: 512 columns = kTcTiles x kTcCols; the 256 hidden units of a net are produced in 256 / kTcCols rounds.
+// TILES = 128-env groups per CTA: 4 (512 environment threads, TMEM 4 x 128 columns, two rounds per net) for large
+// shards, 2 (256 threads, 2 x 256 columns, one round per net) for shards that would otherwise leave SMs empty.
+constexpr int kTcBFloats = tc::kTileN * tc::kK;              // 6,144 floats per B operand
+constexpr int kTcW2Off = 4 * kTcBFloats;                     // [actor hi | actor lo | critic hi | critic lo]
+constexpr int kTcW2cOff = kTcW2Off + kHidden * 10;           // W2 actor as [j][5] pairs, then w2c[j]
+constexpr int kTcTailOff = kTcW2cOff + kHidden;              // b2[0..9], b2c, pad
+constexpr int kTcWeightFloats = kTcTailOff + 12;             // 27,404 floats
+
+// Packing of the reference network's parameters (nn.Linear layout: weight [out][in], lib/model.py:10-26) into the
+// two layouts above, one thread per packed float: runs after every optimiser epoch, so it is one launch and not
+// forty small tensor operations (13 ms per epoch in PyTorch, as much as the rollout of 32,768 envs x 1,024 steps).
+template <bool TC>
+__global__ void __launch_bounds__(256)
+k_pack_policy(const float *__restrict__ w1a, const float *__restrict__ b1a, const float *__restrict__ w2a,
+              const float *__restrict__ b2a, const float *__restrict__ w1c, const float *__restrict__ b1c,
+              const float *__restrict__ w2c, const float *__restrict__ b2c, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float v = 0.0f;
+    if (TC) {
+        if (i >= kTcWeightFloats) return;
+        if (i < 4 * kTcBFloats) {                            // [actor hi | actor lo | critic hi | critic lo], UMMA layout
+            const int which = i / kTcBFloats, r = i % kTcBFloats;
+            const int j = (r / 192) * 8 + (r % 32) / 4, k = ((r % 192) / 32) * 4 + r % 4;
+            const float *w1 = which < 2 ? w1a : w1c, *b1 = which < 2 ? b1a : b1c;
+            const float x = k < kObsDim ? w1[j * kObsDim + k] : (k == kObsDim ? b1[j] : 0.0f);
+            const float hi = tc::to_tf32(x);
+            v = (which & 1) ? tc::to_tf32(x - hi) : hi;
+        } else if (i < kTcW2cOff) {                          // actor second layer as [j][10] (q = 9 is padding)
+            const int r = i - kTcW2Off, j = r / 10, q = r % 10;
+            v = q < kActions ? w2a[q * kHidden + j] : 0.0f;
+        } else if (i < kTcTailOff) {
+            v = w2c[i - kTcW2cOff];
+        } else {
+            const int r = i - kTcTailOff;                    // b2[0..8], 0, b2c, 0
+            v = r < kActions ? b2a[r] : (r == 10 ? b2c[0] : 0.0f);
+        }
+    } else {
+        if (i >= kPolicyFloats) return;
+        constexpr int kBody = (kHidden / 2) * kPairFloats;
+        if (i < kBody) {
+            const int p = i / kPairFloats, r = i % kPairFloats;   // pair of hidden units (2p, 2p + 1)
+            const bool critic = r >= kActorPairFloats;
+            const int c = critic ? r - kActorPairFloats : r;
+            const float *w1 = critic ? w1c : w1a, *b1 = critic ? b1c : b1a;
+            if (c < 36) v = w1[(2 * p + (c & 1)) * kObsDim + (c >> 1)];
+            else if (c < 38) v = b1[2 * p + (c - 36)];
+            else if (c >= 40) {
+                const int d = c - 40;
+                if (!critic) {                               // (W2[2q][j], W2[2q+1][j]) for j = 2p, 2p + 1
+                    const int q = d >> 2, sft = (d >> 1) & 1, rr = d & 1, row = 2 * q + rr;
+                    v = row < kActions ? w2a[row * kHidden + 2 * p + sft] : 0.0f;
+                } else if (d < 2) {
+                    v = w2c[2 * p + d];
+                }
+            }
+        } else {
+            const int r = i - kBody;
+            v = r < kActions ? b2a[r] : (r == 10 ? b2c[0] : 0.0f);
+        }
+    }
+    out[i] = v;
+}
+
+template <int U, int TILES>
+__global__ void __launch_bounds__(TILES * 128 + 32, 1)
+k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const float *__restrict__ weights,
+                    int n_envs, int n_steps, int env_offset, unsigned long long seed, unsigned long long step0,
+                    double2 *__restrict__ pos, double2 *__restrict__ vel, int4 *__restrict__ ints,
+                    float *__restrict__ cur_obs, float *__restrict__ cur_term, float *__restrict__ cur_trunc,
+                    double reward_scale, float *__restrict__ obs_buf, float *__restrict__ act_buf,
+                    float *__restrict__ rew_buf, float *__restrict__ val_buf, float *__restrict__ term_buf,
+                    float *__restrict__ trunc_buf, float *__restrict__ logp_buf, float *__restrict__ last_val,
+                    float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes, int obs_mode) {
+    constexpr int kTcTiles = TILES;                          // 128-env groups per CTA (+ one MMA-issuing warp)
+    constexpr int kTcCols = 512 / TILES;                     // accumulator columns per group and round
+    constexpr int kTcRounds = kHidden / kTcCols;             // rounds per net
+    static_assert(TILES == 2 || TILES == 4, "TMEM: 512 columns = TILES x (256 or 128)");
+    extern __shared__ __align__(16) unsigned char smem[];
+    // [tables | pad to a 128-byte boundary | weights | A tiles (hi, lo per group)]
+    const int w_off = (int)((tc::smem_u32(smem) + (uint32_t)table_bytes + 127u) / 128u * 128u - tc::smem_u32(smem));
+    float *sw = reinterpret_cast<float *>(smem + w_off);
+    unsigned char *sA = smem + w_off + ((kTcWeightFloats * 4 + 127) / 128 * 128);
+    // per 128-env group: "accumulator ready" (MMA -> group), "accumulator consumed" and "operand rows written"
+    // (group -> MMA issuer).  Groups never wait for each other: no CTA-wide barrier inside the step loop.
+    __shared__ __align__(8) unsigned long long mbar_full[kTcTiles], mbar_cons[kTcTiles], mbar_rows[kTcTiles];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < kTcWeightFloats / 4; i += blockDim.x)
+        reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(weights)[i];
+    if (tid == 0)
+        for (int g = 0; g < kTcTiles; ++g) {
+            tc::mbar_init(tc::smem_u32(&mbar_full[g]), 1);
+            tc::mbar_init(tc::smem_u32(&mbar_cons[g]), 128);
+            tc::mbar_init(tc::smem_u32(&mbar_rows[g]), 128);
+        }
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);      // ends with __syncthreads()
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    const uint32_t sB = tc::smem_u32(sw);
+    const uint32_t idesc = tc::make_idesc_tf32(128, kTcCols);
+    const int n_forward = n_steps + (last_val ? 1 : 0);      // forward passes per thread
+
+    if (warp == kTcTiles * 4) {
+        // ===== MMA issuer (one elected lane): runs ahead of the groups, throttled only by the barriers =====
+        if ((tid & 31) == 0) {
+            uint32_t p_rows = 0, p_cons = 0;                 // same phase for every group: all advance in lock step here
+            for (int f = 0; f < n_forward; ++f) {
+#pragma unroll 1
+                for (int rnd = 0; rnd < 2 * kTcRounds; ++rnd) {
+                    const int net = rnd / kTcRounds, part = rnd % kTcRounds;
+                    const uint32_t bh = sB + (uint32_t)((2 * net) * kTcBFloats * 4 + part * (kTcCols / 8) * tc::kSBO);
+                    const uint32_t bl = bh + (uint32_t)(kTcBFloats * 4);
+#pragma unroll 1
+                    for (int g = 0; g < kTcTiles; ++g) {
+                        if (rnd == 0) tc::mbar_wait(tc::smem_u32(&mbar_rows[g]), p_rows);      // this step's rows
+                        if (f > 0 || rnd > 0) tc::mbar_wait(tc::smem_u32(&mbar_cons[g]), p_cons);  // D_g read out
+                        tc::tc_fence_after();
+                        const uint32_t ah = tc::smem_u32(sA + g * 2 * tc::kABytes), al = ah + tc::kABytes;
+                        const uint32_t d = tbase + (uint32_t)(g * kTcCols);
+#pragma unroll
+                        for (int pr = 0; pr < 3; ++pr) {
+                            const uint32_t a0 = (pr == 1) ? al : ah, b0 = (pr == 2) ? bl : bh;
+#pragma unroll
+                            for (int ks = 0; ks < tc::kK / 8; ++ks)
+                                tc::mma_tf32(d, tc::make_smem_desc(a0 + ks * 2 * tc::kLBO),
+                                             tc::make_smem_desc(b0 + ks * 2 * tc::kLBO), idesc, (pr | ks) != 0);
+                        }
+                        tc::mma_commit(tc::smem_u32(&mbar_full[g]));
+                    }
+                    if (rnd == 0) p_rows ^= 1u;
+                    if (f > 0 || rnd > 0) p_cons ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== environment threads: one thread = one environment = one TMEM lane of its group =====
+        const int group = tid >> 7, row = tid & 127;
+        const uint32_t my_tmem = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(group * kTcCols);
+        unsigned char *myA = sA + group * 2 * tc::kABytes;   // hi tile, then lo tile
+        const uint32_t full_bar = tc::smem_u32(&mbar_full[group]), cons_bar = tc::smem_u32(&mbar_cons[group]);
+        const uint32_t rows_bar = tc::smem_u32(&mbar_rows[group]);
+        uint32_t parity = 0;
+
+        const int e_raw = blockIdx.x * (kTcTiles * 128) + tid;
+        const bool active = e_raw < n_envs;
+        const int e = active ? e_raw : n_envs - 1;           // idle threads shadow the last env (no stores)
+
+        EnvState s;
+        {
+            const double2 p = pos[e], v = vel[e];
+            const int4 q = ints[e];
+            s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
+            s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
+        }
+        float obs[kObsDim];
+        {
+            const float2 *src = reinterpret_cast<const float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+            for (int i = 0; i < kObsDim / 2; ++i) { const float2 v = src[i]; obs[2 * i] = v.x; obs[2 * i + 1] = v.y; }
+        }
+        float tc_ = cur_term[e], uc = cur_trunc[e];
+        const uint32_t gid = (uint32_t)(env_offset + e);
+
+        // one forward pass of both nets for the observation in `obs`
+        auto forward = [&](PolicyOut &po) {
+            // this thread's operand row: obs | 1 | 0...  split into TF32 hi and lo.  The previous pass's MMAs have
+            // completed (their last "accumulator ready" was awaited), so the tile may be overwritten.
+#pragma unroll
+            for (int c = 0; c < tc::kKChunks; ++c) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 4 * c + j;
+                    const float x = k < kObsDim ? obs[k < kObsDim ? k : 0] : (k == kObsDim ? 1.0f : 0.0f);
+                    hi[j] = tc::to_tf32(x);
+                    lo[j] = tc::to_tf32(x - hi[j]);
+                }
+                const int off = tc::operand_offset(row, 4 * c);
+                *reinterpret_cast<float4 *>(myA + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(myA + tc::kABytes + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            tc::fence_async_smem();
+            tc::mbar_arrive(rows_bar);
+            float2 L[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) L[q] = make_float2(0.0f, 0.0f);
+            float2 V = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+            for (int rnd = 0; rnd < 2 * kTcRounds; ++rnd) {
+                const int net = rnd / kTcRounds, part = rnd % kTcRounds;   // net 0 = actor, 1 = critic
+                tc::mbar_wait(full_bar, parity);
+                parity ^= 1u;
+                tc::tc_fence_after();
+                if (net == 0) {
+                    const float2 *w2 = reinterpret_cast<const float2 *>(sw + kTcW2Off) + (size_t)(part * kTcCols) * 5;
+#pragma unroll 1
+                    for (int c = 0; c < kTcCols; c += 16) {
+                        float v[16];
+                        tc::tmem_ld16(my_tmem + c, v);
+                        if (c + 16 == kTcCols) { tc::tc_fence_before(); tc::mbar_arrive(cons_bar); }   // D_g is free again
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float h = fmaxf(v[i], 0.0f);
+#pragma unroll
+                            for (int q = 0; q < 5; ++q) L[q] = __ffma2_rn(make_float2(h, h), w2[(c + i) * 5 + q], L[q]);
+                        }
+                    }
+                } else {
+                    const float4 *wc = reinterpret_cast<const float4 *>(sw + kTcW2cOff + part * kTcCols);
+#pragma unroll 1
+                    for (int c = 0; c < kTcCols; c += 16) {
+                        float v[16];
+                        tc::tmem_ld16(my_tmem + c, v);
+                        if (c + 16 == kTcCols) { tc::tc_fence_before(); tc::mbar_arrive(cons_bar); }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 w4 = wc[c / 4 + i];
+                            V = __ffma2_rn(make_float2(fmaxf(v[4 * i], 0.0f), fmaxf(v[4 * i + 1], 0.0f)),
+                                           make_float2(w4.x, w4.y), V);
+                            V = __ffma2_rn(make_float2(fmaxf(v[4 * i + 2], 0.0f), fmaxf(v[4 * i + 3], 0.0f)),
+                                           make_float2(w4.z, w4.w), V);
+                        }
+                    }
+                }
+            }
+            const float *tail = sw + kTcTailOff;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                po.logit[2 * q] = L[q].x + tail[2 * q];
+                po.logit[2 * q + 1] = L[q].y + tail[2 * q + 1];
+            }
+            po.value = (V.x + V.y) + tail[10];
+        };
+
+        PolicyOut po;
+        for (int t = 0; t < n_steps; ++t) {
+            const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+            forward(po);
+            const unsigned long long gs = step0 + (unsigned long long)t;
+            const uint32_t bits = philox_uniform_bits((uint32_t)seed, (uint32_t)(seed >> 32), gid, (uint32_t)gs,
+                                                      (uint32_t)(gs >> 32), 0x43415245u);
+            const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
+            float logp, us;
+            const int a = sample_action(po, u, logp, us);
+            if (active) {
+                if (obs_mode == kObsPose) {
+                    store_pose(reinterpret_cast<PoseRec *>(obs_buf) + idx, s, obs[2], obs[3]);
+                } else {
+                    float2 *dst = reinterpret_cast<float2 *>(obs_buf + idx * kObsDim);
+#pragma unroll
+                    for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+                }
+                act_buf[idx] = (float)a;
+                val_buf[idx] = po.value;
+                logp_buf[idx] = logp;
+                term_buf[idx] = tc_;
+                trunc_buf[idx] = uc;
+                if (u_dbg) u_dbg[idx] = u;
+            }
+            StepResult o;
+            env_step<U>(s, a, reward_scale, P, T, o, active ? stats : nullptr);
+            if (active) rew_buf[idx] = o.reward;
+#pragma unroll
+            for (int i = 0; i < kObsDim; ++i) obs[i] = o.obs[i];
+            tc_ = o.terminated ? 1.0f : 0.0f;
+            uc = o.truncated ? 1.0f : 0.0f;
+        }
+        if (last_val) forward(po);                           // bootstrap value of the final observation
+        if (active) {
+            pos[e] = make_double2(s.px, s.py);
+            vel[e] = make_double2(s.vx, s.vy);
+            ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+            float2 *dst = reinterpret_cast<float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+            for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+            cur_term[e] = tc_;
+            cur_trunc[e] = uc;
+            if (last_val) last_val[e] = po.value;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tbase);
+}

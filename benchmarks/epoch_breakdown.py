@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--envs", type=int, default=32768)
     ap.add_argument("--epochs", type=int, default=6)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--per-minibatch", action="store_true", help="three launches per minibatch instead of carenv_ppo_epoch")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     n, T, B = args.envs, 1024, 512
@@ -50,15 +51,18 @@ def main():
             ev[4].record()
             obs_b, act_b, val_b, logp_b = buf.get()
             obs_f, act_f, logp_f, adv_f, ret_f = obs_b.view(-1, 18), act_b.view(-1), logp_b.view(-1), adv.view(-1), ret.view(-1)
-            for _ in range(80):
-                torch.randint(0, T * n, (B,), device=dev, out=idx)
-                upd.grad(obs_f, idx, act_f, logp_f, adv_f, ret_f)
-                upd.apply(1)
+            if args.per_minibatch:
+                for _ in range(80):
+                    torch.randint(0, T * n, (B,), device=dev, out=idx)
+                    upd.grad(obs_f, idx, act_f, logp_f, adv_f, ret_f)
+                    upd.apply(1)
+            else:
+                upd.run_epoch(obs_f, torch.randint(0, T * n, (80, B), device=dev), act_f, logp_f, adv_f, ret_f)
             ev[5].record()
         torch.cuda.synchronize()
         t = [ev[i].elapsed_time(ev[i + 1]) for i in range(5)]
         row = {"epoch": epoch, "envs": n, "pack_ms": t[0], "rollout_ms": t[1], "gae_ms": t[2], "stats_ms": t[3],
-               "updates_ms": t[4], "total_ms": sum(t), "rollout_env_steps_per_s": n * T / (t[1] * 1e-3)}
+               "updates_ms": t[4], "update_path": "per-minibatch" if args.per_minibatch else "epoch kernel", "total_ms": sum(t), "rollout_env_steps_per_s": n * T / (t[1] * 1e-3)}
         print(json.dumps(row), flush=True)
         rows.append(row)
     if args.out:

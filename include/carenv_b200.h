@@ -252,6 +252,31 @@ int carenv_ppo_adam(float *w1_actor, float *b1_actor, float *w2_actor, float *b2
                     double eps, double max_grad_norm, const float *scratch, int batch, double vf_coef,
                     double ent_coef, float *sums4, void *stream);
 
+/* All minibatch updates of one PPO epoch in ONE persistent cooperative launch (csrc/ppo_epoch.cuh; replaces the
+ * loops of train.py:223-261 — `for _ in range(train_iters): for start in range(0, n_steps, batch_size): ...` — and,
+ * with several GPUs, the gradient all-reduce between backward and optimizer.step()).
+ *   idx          device int64 [n_updates][batch]: the sample rows of every minibatch, in order
+ *   workspace    device float[carenv_ppo_epoch_workspace_floats()]
+ *   sync_words   device int[2]: grid-barrier counter (cleared by the call) and an error word that stays 0 unless a
+ *                wait inside the kernel ran out of time (a peer rank that never launched)
+ *   comm         NULL on one GPU; otherwise a communicator from carenv_ppo_comm_create + _connect.  The gradient
+ *                slices are exchanged through IPC-mapped peer buffers over NVLink inside the kernel and summed in rank
+ *                order, so every rank applies bit-identical updates; every rank must make the same sequence of calls.
+ *   n_ctas       0 = default (64, or ceil(batch / 8) if larger); must be the same on every rank
+ * Other arguments as carenv_ppo_grad / carenv_ppo_adam. */
+#define CARENV_IPC_HANDLE_BYTES 64
+int carenv_ppo_comm_create(int world, int rank, void **comm, unsigned char *ipc_handle_out /* [64] */);
+int carenv_ppo_comm_connect(void *comm, const unsigned char *all_handles /* [world][64], rank order */);
+int carenv_ppo_comm_destroy(void *comm);
+int carenv_ppo_epoch_workspace_floats(void);
+int carenv_ppo_epoch(float *w1_actor, float *b1_actor, float *w2_actor, float *b2_actor, float *w1_critic,
+                     float *b1_critic, float *w2_critic, float *b2_critic, const float *obs, const long long *idx,
+                     const float *act, const float *old_logp, const float *adv, const float *ret, int batch,
+                     int n_updates, double clip_ratio, double vf_coef, double ent_coef, float *exp_avg,
+                     float *exp_avg_sq, const float *lr, int *step, double beta1, double beta2, double eps,
+                     double max_grad_norm, float *sums4, float *workspace, int *sync_words, void *comm, int n_ctas,
+                     void *stream);
+
 /* Test hook for the tensor-core building blocks (csrc/tc_mlp.cuh): D[128][256] = A[128][24] * B[256][24]^T,
  * tcgen05.mma kind::tf32 with the accumulator in tensor memory; device pointers, row-major float32. */
 int carenv_tc_gemm_test(const float *A, const float *B, float *D, void *stream);

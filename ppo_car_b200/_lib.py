@@ -15,7 +15,7 @@ ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("CARENV_LIB") or os.path.join(_PKG, "libcarenv_b200.so")   # override: kernel experiments
 SOURCES = [os.path.join(_PKG, "csrc", f)
            for f in ("carenv_kernels.cu", "carenv_core.cuh", "carenv_tables.h", "policy_core.cuh", "tc_mlp.cuh",
-                     "ppo_update.cuh", "policy_rollout.cuh", "policy_abi.cuh")]
+                     "ppo_update.cuh", "ppo_epoch.cuh", "policy_rollout.cuh", "policy_abi.cuh")]
 HEADER = os.path.join(ROOT, "include", "carenv_b200.h")
 
 ACT_U8, ACT_I32, ACT_I64 = 0, 1, 2
@@ -92,6 +92,16 @@ def lib():
     L.carenv_ppo_grad.restype = i32
     L.carenv_ppo_adam.argtypes = [vp] * 8 + [vp, f64, vp, vp, vp, vp, f64, f64, f64, f64, vp, i32, f64, f64, vp, vp]
     L.carenv_ppo_adam.restype = i32
+    L.carenv_ppo_comm_create.argtypes = [i32, i32, C.POINTER(vp), vp]
+    L.carenv_ppo_comm_create.restype = i32
+    L.carenv_ppo_comm_connect.argtypes = [vp, vp]
+    L.carenv_ppo_comm_connect.restype = i32
+    L.carenv_ppo_comm_destroy.argtypes = [vp]
+    L.carenv_ppo_comm_destroy.restype = i32
+    L.carenv_ppo_epoch_workspace_floats.restype = i32
+    L.carenv_ppo_epoch.argtypes = [vp] * 8 + [vp] * 6 + [i32, i32, f64, f64, f64, vp, vp, vp, vp, f64, f64, f64, f64,
+                                                         vp, vp, vp, vp, i32, vp]
+    L.carenv_ppo_epoch.restype = i32
     L.carenv_pack_policy.argtypes = [i32] + [vp] * 10
     L.carenv_pack_policy.restype = i32
     L.carenv_policy_weights_floats.restype = i32

@@ -33,6 +33,7 @@
 #include "carenv_tables.h"
 #include "policy_core.cuh"
 #include "ppo_update.cuh"
+#include "ppo_epoch.cuh"
 #include "tc_mlp.cuh"
 
 using namespace carenv;

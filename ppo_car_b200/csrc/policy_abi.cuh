@@ -62,6 +62,121 @@ int carenv_ppo_adam(float *w1a, float *b1a, float *w2a, float *b2a, float *w1c, 
     return 0;
 }
 
+/* ---- all minibatch updates of an epoch in one persistent launch (csrc/ppo_epoch.cuh) ---- */
+struct PpoComm {
+    int world = 1, rank = 0, device = 0;
+    ppo::Exchange *local = nullptr;
+    ppo::Exchange *peer[ppo::kMaxWorld] = {};
+    unsigned long long seq = 0;           // updates completed so far (advances identically on every rank)
+};
+
+int carenv_ppo_comm_create(int world, int rank, void **comm, unsigned char *ipc_handle_out) {
+    if (!comm || !ipc_handle_out) return fail(CARENV_E_INVAL, "null pointer");
+    *comm = nullptr;
+    if (world < 1 || world > ppo::kMaxWorld || rank < 0 || rank >= world)
+        return fail(CARENV_E_INVAL, "world must be 1..8 and rank in [0, world)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CARENV_IPC_HANDLE_BYTES, "handle size");
+    PpoComm *c = new PpoComm();
+    c->world = world; c->rank = rank;
+    if (cudaGetDevice(&c->device) != cudaSuccess) { delete c; return fail(CARENV_E_NOGPU, "no CUDA device"); }
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&c->local), sizeof(ppo::Exchange));
+    if (e == cudaSuccess) e = cudaMemset(c->local, 0, sizeof(ppo::Exchange));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->local);
+    if (e != cudaSuccess) {
+        if (c->local) cudaFree(c->local);
+        delete c;
+        return cuda_fail(e, "carenv_ppo_comm_create");
+    }
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    c->peer[rank] = c->local;
+    *comm = c;
+    return 0;
+}
+
+int carenv_ppo_comm_connect(void *comm, const unsigned char *all_handles) {
+    PpoComm *c = static_cast<PpoComm *>(comm);
+    if (!c || !all_handles) return fail(CARENV_E_INVAL, "null pointer");
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the communicator's CUDA device");
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank || c->peer[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all_handles + (size_t)r * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer[r] = static_cast<ppo::Exchange *>(p);
+    }
+    return 0;
+}
+
+int carenv_ppo_comm_destroy(void *comm) {
+    PpoComm *c = static_cast<PpoComm *>(comm);
+    if (!c) return 0;
+    DeviceGuard guard(c->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; ++r)
+        if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    if (c->local) cudaFree(c->local);
+    delete c;
+    return 0;
+}
+
+int carenv_ppo_epoch_workspace_floats(void) { return ppo::kMaxCtas * ppo::kLocalPad + 2 * ppo::kMaxCtas + 8 * ppo::kMaxCtas; }
+
+int carenv_ppo_epoch(float *w1a, float *b1a, float *w2a, float *b2a, float *w1c, float *b1c, float *w2c, float *b2c,
+                     const float *obs, const long long *idx, const float *act, const float *old_logp,
+                     const float *adv, const float *ret, int batch, int n_updates, double clip_ratio, double vf_coef,
+                     double ent_coef, float *exp_avg, float *exp_avg_sq, const float *lr, int *step, double beta1,
+                     double beta2, double eps, double max_grad_norm, float *sums4, float *workspace, int *sync_words,
+                     void *comm, int n_ctas, void *stream) {
+    if (batch < 2 || batch > ppo::kMaxBatch) return fail(CARENV_E_INVAL, "batch must be in 2..1024");
+    if (n_updates < 0) return fail(CARENV_E_INVAL, "negative n_updates");
+    if (!w1a || !b1a || !w2a || !b2a || !w1c || !b1c || !w2c || !b2c || !obs || !idx || !act || !old_logp || !adv ||
+        !ret || !exp_avg || !exp_avg_sq || !lr || !step || !sums4 || !workspace || !sync_words)
+        return fail(CARENV_E_INVAL, "null pointer");
+    if (n_updates == 0) return 0;
+    PpoComm *c = static_cast<PpoComm *>(comm);
+    int G = n_ctas > 0 ? n_ctas : 64;
+    const int need = (batch + ppo::kEpochSamples - 1) / ppo::kEpochSamples;
+    if (G < need) G = need;
+    if (G < ppo::kMinCtas || G > ppo::kMaxCtas) return fail(CARENV_E_INVAL, "n_ctas must be in 49..160");
+    int dev = 0, sms = 0, coop = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop || G > sms) return fail(CARENV_E_INVAL, "the device cannot keep the update grid resident");
+    ppo::EpochArgs A;
+    memset(&A, 0, sizeof(A));
+    A.P = ppo::MutableParams{w1a, b1a, w2a, b2a, w1c, b1c, w2c, b2c};
+    A.obs = obs; A.idx = idx; A.act = act; A.old_logp = old_logp; A.adv = adv; A.ret = ret;
+    A.B = batch; A.n_updates = n_updates;
+    A.clip_ratio = (float)clip_ratio; A.vf_coef = (float)vf_coef; A.ent_coef = (float)ent_coef;
+    A.max_grad_norm = (float)max_grad_norm; A.beta1 = (float)beta1; A.beta2 = (float)beta2; A.eps = (float)eps;
+    A.m = exp_avg; A.v = exp_avg_sq; A.lr = lr; A.step = step; A.sums4 = sums4;
+    A.partial = workspace;
+    A.ssq = workspace + (size_t)ppo::kMaxCtas * ppo::kLocalPad;
+    A.stat = A.ssq + 2 * ppo::kMaxCtas;
+    A.bar = reinterpret_cast<unsigned int *>(sync_words);
+    A.err = sync_words + 1;
+    A.world = 1; A.rank = 0;
+    if (c && c->world > 1) {
+        if (c->device != dev) return fail(CARENV_E_INVAL, "the communicator belongs to another device");
+        for (int r = 0; r < c->world; ++r)
+            if (!c->peer[r]) return fail(CARENV_E_INVAL, "communicator not connected (carenv_ppo_comm_connect)");
+        A.world = c->world; A.rank = c->rank; A.seq_base = c->seq;
+        for (int r = 0; r < c->world; ++r) A.peer[r] = c->peer[r];
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(cudaMemsetAsync(sync_words, 0, sizeof(int), st));
+    void *args[] = {&A};
+    CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(ppo::k_ppo_epoch<ppo::kEpochSamples>), dim3(G),
+                                   dim3(ppo::kEpochThreads), args, 0, st));
+    if (c) c->seq += (unsigned long long)n_updates;
+    return 0;
+}
+
 int carenv_policy_weights_floats(void) { return kPolicyFloats; }
 
 int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs, int n_steps, int env_offset,

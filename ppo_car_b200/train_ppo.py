@@ -98,6 +98,9 @@ def parse_args(argv=None):
     p.add_argument("--fused-update", action="store_true",
                    help="one minibatch update = three kernel launches (carenv_ppo_grad / carenv_ppo_adam: forward, "
                         "loss, backward, clip, Adam for the reference network) instead of a PyTorch autograd graph")
+    p.add_argument("--per-minibatch-update", action="store_true",
+                   help="with --fused-update: three launches (+ one NCCL all-reduce) per minibatch instead of ONE "
+                        "persistent launch per epoch with the gradient all-reduce over NVLink peer memory inside it")
     p.add_argument("--compact-obs", action="store_true",
                    help="with --fused-rollout: store 32-byte pose records instead of observations and recompute the "
                         "minibatch observations in the update (VecCarEnv.observe)")
@@ -135,6 +138,11 @@ def train(args) -> list[dict]:
 
         fused_upd = FusedPPOUpdate(agent.actor, agent.critic, args.batch_size, args.learning_rate, args.clip_ratio,
                                    args.vf_coef, args.ent_coef, args.max_grad_norm)
+    # all minibatch updates of an epoch in one persistent launch (csrc/ppo_epoch.cuh); it reads observation rows, so
+    # pose-record storage keeps the per-minibatch kernels
+    epoch_kernel = fused_upd is not None and not args.per_minibatch_update and not args.compact_obs
+    if epoch_kernel and world > 1:
+        fused_upd.connect()                                 # IPC-mapped gradient exchange buffers of the peers
     if graph_update:                                        # capturable Adam with the learning rate in a tensor
         opt = torch.optim.Adam(agent.parameters(), lr=torch.tensor(args.learning_rate, device=dev), eps=1e-5,
                                capturable=True)
@@ -266,7 +274,7 @@ def train(args) -> list[dict]:
                     sums.add_(torch.stack([pol.detach(), vl.detach(), e.detach(), loss.detach()]))
 
                 update_graph = None
-                if graph_update:                                # obs_f, act_f, ... are views of the static buffer tensors
+                if graph_update and not epoch_kernel:           # obs_f, act_f, ... are views of the static buffer tensors
                     side = torch.cuda.Stream(device=dev)
                     side.wait_stream(torch.cuda.current_stream(dev))
                     with torch.cuda.stream(side):
@@ -280,7 +288,10 @@ def train(args) -> list[dict]:
             sums.zero_()
             if fused_upd is not None:
                 fused_upd.sums.zero_()
-            for _ in range(args.train_iters * n_mb):
+            if epoch_kernel:
+                idx_all = torch.randint(0, T * n, (args.train_iters * n_mb, args.batch_size), device=dev)
+                fused_upd.run_epoch(obs_f, idx_all, act_f, logp_f, adv_f, ret_f, world=world)
+            for _ in range(0 if epoch_kernel else args.train_iters * n_mb):
                 if update_graph is not None:
                     update_graph.replay()
                 else:
@@ -311,6 +322,9 @@ def train(args) -> list[dict]:
                 save_checkpoint(f"checkpoint_{epoch}.dat")
     finally:                                               # train.py:294-301
         save_checkpoint("model.dat")
+    if fused_upd is not None:
+        fused_upd.check_epoch()
+        fused_upd.close()
     envs.close()
     return history
 

@@ -61,3 +61,39 @@ def test_two_rank_sharded_rollout_equals_single_rank(tracks_dir):
     for r in res:                                                       # both ranks hold the global statistics
         assert np.isclose(r[4][0], full["rew"].sum()) and r[4][1] == full["rew"].size
         assert r[4][2] == full["term"].sum() + full["trunc"].sum()
+
+
+def _handle_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ppo_car_b200.ppo_update import exchange_ipc_handles
+
+    mine = bytes([rank + 1]) * 64                          # stands in for this rank's cudaIpcMemHandle_t
+    everyone = exchange_ipc_handles(mine)
+    bad = None
+    try:
+        exchange_ipc_handles(b"short")
+    except ValueError as e:
+        bad = str(e)
+    q.put((rank, everyone, bad))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ipc_handle_exchange_is_in_rank_order():
+    """Host side of the in-kernel gradient all-reduce (FusedPPOUpdate.connect): every rank ends up with all the
+    64-byte handles concatenated in rank order — what carenv_ppo_comm_connect indexes by rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_handle_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = bytes([1]) * 64 + bytes([2]) * 64
+    for rank, everyone, bad in res:
+        assert everyone == want and bad is not None

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Fused rollout kernels versus shard size: CUDA-core kernel and the tensor-core kernel with 2 or 4
-128-env groups per CTA (option tc_tiles).  One JSON line per size."""
+128-env groups per CTA or 2 groups with a helper thread per environment (option tc_tiles 2 / 4 / 3).  One JSON line per size."""
 import json
 import os
 import sys
@@ -17,13 +17,17 @@ torch.manual_seed(0)
 net = ActorCritic(18, 9).to(dev)
 packed_cc = ppo_car_b200.pack_policy_weights(net.actor, net.critic)
 packed_tc = ppo_car_b200.pack_policy_weights_tc(net.actor, net.critic)
-for n, T in ((4096, 256), (8192, 256), (16384, 128), (32768, 128), (65536, 64), (131072, 64), (262144, 32), (1048576, 16)):
+SIZES = ((4096, 256), (8192, 256), (16384, 128), (32768, 128), (65536, 64), (131072, 64), (262144, 32), (1048576, 16))
+if len(sys.argv) > 1:                                       # python benchmarks/fused_tiles.py 32768 1048576
+    SIZES = tuple((n, T) for n, T in SIZES if str(n) in sys.argv[1:])
+for n, T in SIZES:
     env = ppo_car_b200.VecCarEnv(n, track, reward_scaling=0.1, float_flags=True, with_info=False)
     buf = ppo_car_b200.Buffer((18,), T, n, dev)
     obs = env.reset()[0].clone()
     term, trunc, lv = torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.empty(n, device=dev)
     res = {"n_envs": n, "steps_per_launch": T}
-    for tag, packed, tiles in (("cuda_core", packed_cc, 0), ("tc_tiles2", packed_tc, 2), ("tc_tiles4", packed_tc, 4)):
+    for tag, packed, tiles in (("cuda_core", packed_cc, 0), ("tc_tiles2", packed_tc, 2), ("tc_tiles4", packed_tc, 4),
+                              ("tc_2groups_helpers", packed_tc, 3)):
         env.set_option("tc_tiles", tiles)
         for i in range(2):
             ppo_car_b200.fused_rollout(env, packed, buf, obs, term, trunc, seed=1, step0=i * T, last_val=lv)

@@ -42,6 +42,9 @@ def main():
     adv, ret = torch.randn(M, device=dev), torch.randn(M, device=dev)
     idx = torch.randint(0, M, (U, B), device=dev)
 
+    def note(msg):
+        print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     def fresh():
         net = ActorCritic(18, 9).to(dev)
         net.load_state_dict(net0.state_dict())
@@ -72,6 +75,8 @@ def main():
 
     # correctness first: one epoch each from the same start
     per_minibatch()
+    torch.cuda.synchronize()
+    note("per-minibatch reference epoch done")
     rows = []
     for ctas in args.ctas:
         net_b, ub = fresh()
@@ -79,7 +84,8 @@ def main():
             ub.connect()
         ub.run_epoch(obs, idx, act, old_logp, adv, ret, world=world, n_ctas=ctas)
         ub.check_epoch()
-        err = max(float((pa - pb).abs().max()) for pa, pb in zip(ua.params, ub.params))
+        note(f"epoch kernel done (ctas {ctas})")
+        err = max(float((pa.detach() - pb.detach()).abs().max()) for pa, pb in zip(ua.params, ub.params))
         flat = torch.cat([p.detach().reshape(-1) for p in ub.params])
         same = True
         if world > 1:
@@ -88,10 +94,18 @@ def main():
             same = all(torch.equal(gathered[0], g) for g in gathered)
         ms_epoch = timed(lambda: ub.run_epoch(obs, idx, act, old_logp, adv, ret, world=world, n_ctas=ctas), args.reps)
         ub.check_epoch()
-        rows.append({"n_ctas": ctas or 64, "epoch_kernel_ms": ms_epoch, "epoch_kernel_us_per_update": 1e3 * ms_epoch / U,
+        note(f"epoch kernel timed: {ms_epoch:.3f} ms")
+        prof = torch.zeros((U, 4), dtype=torch.int64, device=dev)
+        ub.run_epoch(obs, idx, act, old_logp, adv, ret, world=world, n_ctas=ctas, prof=prof)
+        torch.cuda.synchronize()
+        pr = prof.cpu().double()
+        phase_us = [float((pr[5:, 1] - pr[5:, 0]).mean()) / 1e3, float((pr[5:, 2] - pr[5:, 1]).mean()) / 1e3,
+                    float((pr[5:, 3] - pr[5:, 2]).mean()) / 1e3]
+        rows.append({"n_ctas": ctas or 64, "phase_us_forward_backward|reduce_exchange|adam": phase_us, "epoch_kernel_ms": ms_epoch, "epoch_kernel_us_per_update": 1e3 * ms_epoch / U,
                      "max_abs_param_diff_vs_per_minibatch": err, "ranks_bit_identical": same})
         ub.close()
     ms_mb = timed(per_minibatch, max(1, args.reps // 2))
+    note(f"per-minibatch timed: {ms_mb:.3f} ms")
     g = torch.cuda.CUDAGraph()                             # the per-minibatch path replayed from a CUDA graph (train_ppo --graph-update)
     idx1 = idx[0].clone()
     side = torch.cuda.Stream(device=dev)
@@ -106,13 +120,16 @@ def main():
         for _ in range(U):
             g.replay()
 
+    note("graph captured")
     ms_graph = timed(graphed, max(1, args.reps // 2))
     if rank == 0:
         for r in rows:
             print(json.dumps(dict(r, n_gpus=world, updates=U, batch=B, per_minibatch_ms=ms_mb,
                                   per_minibatch_us_per_update=1e3 * ms_mb / U, per_minibatch_graph_ms=ms_graph,
                                   per_minibatch_graph_us_per_update=1e3 * ms_graph / U)), flush=True)
+    del g                                                   # a live graph with captured NCCL work blocks the teardown
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

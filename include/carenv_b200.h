@@ -260,9 +260,10 @@ int carenv_ppo_adam(float *w1_actor, float *b1_actor, float *w2_actor, float *b2
  *   sync_words   device int[2]: grid-barrier counter (cleared by the call) and an error word that stays 0 unless a
  *                wait inside the kernel ran out of time (a peer rank that never launched)
  *   comm         NULL on one GPU; otherwise a communicator from carenv_ppo_comm_create + _connect.  The gradient
- *                slices are exchanged through IPC-mapped peer buffers over NVLink inside the kernel and summed in rank
+ *                elements are pushed into IPC-mapped peer buffers over NVLink inside the kernel and summed in rank
  *                order, so every rank applies bit-identical updates; every rank must make the same sequence of calls.
  *   n_ctas       0 = default (64, or ceil(batch / 8) if larger); must be the same on every rank
+ *   prof         NULL, or device int64 [n_updates][4]: nanosecond stamps of update start and of the three grid barriers
  * Other arguments as carenv_ppo_grad / carenv_ppo_adam. */
 #define CARENV_IPC_HANDLE_BYTES 64
 int carenv_ppo_comm_create(int world, int rank, void **comm, unsigned char *ipc_handle_out /* [64] */);
@@ -275,7 +276,7 @@ int carenv_ppo_epoch(float *w1_actor, float *b1_actor, float *w2_actor, float *b
                      int n_updates, double clip_ratio, double vf_coef, double ent_coef, float *exp_avg,
                      float *exp_avg_sq, const float *lr, int *step, double beta1, double beta2, double eps,
                      double max_grad_norm, float *sums4, float *workspace, int *sync_words, void *comm, int n_ctas,
-                     void *stream);
+                     long long *prof, void *stream);
 
 /* Test hook for the tensor-core building blocks (csrc/tc_mlp.cuh): D[128][256] = A[128][24] * B[256][24]^T,
  * tcgen05.mma kind::tf32 with the accumulator in tensor memory; device pointers, row-major float32. */

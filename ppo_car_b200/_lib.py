@@ -100,7 +100,7 @@ def lib():
     L.carenv_ppo_comm_destroy.restype = i32
     L.carenv_ppo_epoch_workspace_floats.restype = i32
     L.carenv_ppo_epoch.argtypes = [vp] * 8 + [vp] * 6 + [i32, i32, f64, f64, f64, vp, vp, vp, vp, f64, f64, f64, f64,
-                                                         vp, vp, vp, vp, i32, vp]
+                                                         vp, vp, vp, vp, i32, vp, vp]
     L.carenv_ppo_epoch.restype = i32
     L.carenv_pack_policy.argtypes = [i32] + [vp] * 10
     L.carenv_pack_policy.restype = i32

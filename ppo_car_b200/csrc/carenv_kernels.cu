@@ -1216,7 +1216,7 @@ int carenv_set_option(void *handle, const char *name, int value) {
     if (std::string(name) == "tab") { h->tab = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
     if (std::string(name) == "warp_per_env") { h->warp_per_env = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
     if (std::string(name) == "tc_tiles") {
-        if (value != 0 && value != 2 && value != 4) return fail(CARENV_E_INVAL, "tc_tiles must be 0, 2 or 4");
+        if (value != 0 && (value < 2 || value > 4)) return fail(CARENV_E_INVAL, "tc_tiles must be 0, 2, 3 or 4");
         h->tc_tiles = value; return 0;
     }
     if (std::string(name) == "smem_pad") {

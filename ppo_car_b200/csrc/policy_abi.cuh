@@ -123,14 +123,14 @@ int carenv_ppo_comm_destroy(void *comm) {
     return 0;
 }
 
-int carenv_ppo_epoch_workspace_floats(void) { return ppo::kMaxCtas * ppo::kLocalPad + 2 * ppo::kMaxCtas + 8 * ppo::kMaxCtas; }
+int carenv_ppo_epoch_workspace_floats(void) { return ppo::kMaxCtas * ppo::kLocalPad + 2 * ppo::kMaxCtas + 8 * ppo::kMaxCtas + ppo::kLocalPad; }
 
 int carenv_ppo_epoch(float *w1a, float *b1a, float *w2a, float *b2a, float *w1c, float *b1c, float *w2c, float *b2c,
                      const float *obs, const long long *idx, const float *act, const float *old_logp,
                      const float *adv, const float *ret, int batch, int n_updates, double clip_ratio, double vf_coef,
                      double ent_coef, float *exp_avg, float *exp_avg_sq, const float *lr, int *step, double beta1,
                      double beta2, double eps, double max_grad_norm, float *sums4, float *workspace, int *sync_words,
-                     void *comm, int n_ctas, void *stream) {
+                     void *comm, int n_ctas, long long *prof, void *stream) {
     if (batch < 2 || batch > ppo::kMaxBatch) return fail(CARENV_E_INVAL, "batch must be in 2..1024");
     if (n_updates < 0) return fail(CARENV_E_INVAL, "negative n_updates");
     if (!w1a || !b1a || !w2a || !b2a || !w1c || !b1c || !w2c || !b2c || !obs || !idx || !act || !old_logp || !adv ||
@@ -161,6 +161,7 @@ int carenv_ppo_epoch(float *w1a, float *b1a, float *w2a, float *b2a, float *w1c,
     A.bar = reinterpret_cast<unsigned int *>(sync_words);
     A.err = sync_words + 1;
     A.world = 1; A.rank = 0;
+    A.prof = prof;
     if (c && c->world > 1) {
         if (c->device != dev) return fail(CARENV_E_INVAL, "the communicator belongs to another device");
         for (int r = 0; r < c->world; ++r)
@@ -171,8 +172,10 @@ int carenv_ppo_epoch(float *w1a, float *b1a, float *w2a, float *b2a, float *w1c,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CU(cudaMemsetAsync(sync_words, 0, sizeof(int), st));
     void *args[] = {&A};
+    CU(cudaFuncSetAttribute(ppo::k_ppo_epoch<ppo::kEpochSamples>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            ppo::kEpochSmemBytes));
     CU(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(ppo::k_ppo_epoch<ppo::kEpochSamples>), dim3(G),
-                                   dim3(ppo::kEpochThreads), args, 0, st));
+                                   dim3(ppo::kEpochThreads), args, ppo::kEpochSmemBytes, st));
     if (c) c->seq += (unsigned long long)n_updates;
     return 0;
 }
@@ -249,8 +252,33 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
     // groups per CTA: 2 while 4 would leave SMs without a CTA (one CTA per SM: the weights take 110 KB)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    int tiles = (n_envs + 511) / 512 >= sms ? 4 : 2;
-    if (h->tc_tiles == 2 || h->tc_tiles == 4) tiles = h->tc_tiles;
+    // 3 = two groups with a helper thread per environment (k_policy_rollout_tc2): the latency-bound shards
+    int tiles = (n_envs + 511) / 512 >= sms ? 4 : 3;
+    if (h->tc_tiles >= 2 && h->tc_tiles <= 4) tiles = h->tc_tiles;
+    // second-layer weights -> constant bank (k_policy_rollout_tc2 reads them as uniform operands)
+    CU(cudaMemcpyToSymbolAsync(c_policy_l2, packed_weights + kTcW2Off, sizeof(float) * (kTcWeightFloats - kTcW2Off), 0,
+                               cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    if (tiles == 3) {
+        const size_t smem2 = (size_t)table_bytes + 128 + (size_t)4 * kTcBFloats * 4 +      // first-layer operands only
+                             (size_t)2 * 2 * tc::kABytes + (size_t)2 * 128 * 12 * sizeof(float);
+        if (smem2 > 227 * 1024) return fail(CARENV_E_TRACK, "track tables too large for the tensor-core rollout kernel");
+        const int grid2 = (n_envs + 255) / 256;
+        int U2 = h->force_generic ? 1 : h->host.P.unroll4;
+        if (h->max_unroll > 0 && U2 > h->max_unroll) U2 = (U2 % h->max_unroll == 0) ? h->max_unroll : 1;
+        auto launch2 = [&](auto kern) -> int {
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            kern<<<grid2, 2 * 256 + 32, smem2, static_cast<cudaStream_t>(stream)>>>(
+                h->host.P, h->dev, packed_weights, n_envs, n_steps, env_offset, seed, step0,
+                reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints), cur_obs,
+                cur_term, cur_trunc, reward_scale, obs_buf, act_buf, rew_buf, val_buf, term_buf, trunc_buf, logp_buf,
+                last_val, u_dbg, h->d_stats, table_bytes, h->pose_rows ? kObsPose : kObsFull);
+            CU(cudaGetLastError());
+            return 0;
+        };
+        if (U2 == 4) return launch2(k_policy_rollout_tc2<4>);
+        if (U2 == 2) return launch2(k_policy_rollout_tc2<2>);
+        return launch2(k_policy_rollout_tc2<1>);
+    }
     const size_t smem = (size_t)table_bytes + 128 + (size_t)((kTcWeightFloats * 4 + 127) / 128 * 128) +
                         (size_t)tiles * 2 * tc::kABytes;
     if (smem > 227 * 1024) return fail(CARENV_E_TRACK, "track tables too large for the tensor-core rollout kernel");

@@ -432,3 +432,324 @@ k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<512>(tbase);
 }
+
+// ---- fused rollout, tensor cores, TWO threads per environment ---------------------------------------------------
+// k_policy_rollout_tc walks one dependent chain of ~6,900 instructions per environment and step (operand row ->
+// MMA -> 256 + 256 hidden units through the CUDA-core second layer -> sampling -> env step); with one 256-env CTA
+// per SM (shards of 32,768 envs, BASELINE config 5) that chain IS the step time, and its second layer also keeps
+// the shared-memory pipe busy for 10k of a step's 28k cycles (every warp streams the same 10 KB of weights: a
+// wavefront per 8 bytes).  Here every environment has an environment thread and a policy thread:
+//   environment thread   operand row, Buffer rows, Philox — then waits for the logits — sampling, env step
+//   policy thread        owns the environment's TMEM lane: ReLU + 256 -> 9 second layer with the weights as UNIFORM
+//                        operands from the constant bank (LDCU: no shared-memory traffic, no per-thread load),
+//                        logits to the environment thread through shared memory; then the whole critic and the
+//                        value row, off the critical path (it runs while the environment thread samples and steps)
+//   issuer lane          a polling state machine per 128-env group: actor MMAs as two N = 128 halves with their own
+//                        commit barriers (the policy threads start after the first half), the critic's N = 256
+//                        MMAs as soon as the actor columns are read out
+// Both nets sum their 256 products in the order of the other kernels: same logit, log-prob and value bits.
+// (The policy threads' loop is free of data-dependent control flow; that is what lets the compiler keep its
+// weight addresses in uniform registers — inside the environment threads' loop it falls back to per-thread LDC.)
+__constant__ __align__(16) float c_policy_l2[kTcWeightFloats - kTcW2Off];   // [unit][5] float2 | w2c[256] | tail[12]
+constexpr int kL2W2c = kTcW2cOff - kTcW2Off, kL2Tail = kTcTailOff - kTcW2Off;
+
+#ifdef CARENV_TC2_PROF          // per-phase cycle counts of one environment / policy thread (kernel tuning builds only)
+#define TC2_T(i) do { const long long now_ = clock64(); prof_[i] += now_ - last_; last_ = now_; } while (0)
+#else
+#define TC2_T(i) do { } while (0)
+#endif
+template <int U>
+__global__ void __launch_bounds__(2 * 256 + 32, 1)
+k_policy_rollout_tc2(const __grid_constant__ TrackParams P, const Tables G, const float *__restrict__ weights,
+                     int n_envs, int n_steps, int env_offset, unsigned long long seed, unsigned long long step0,
+                     double2 *__restrict__ pos, double2 *__restrict__ vel, int4 *__restrict__ ints,
+                     float *__restrict__ cur_obs, float *__restrict__ cur_term, float *__restrict__ cur_trunc,
+                     double reward_scale, float *__restrict__ obs_buf, float *__restrict__ act_buf,
+                     float *__restrict__ rew_buf, float *__restrict__ val_buf, float *__restrict__ term_buf,
+                     float *__restrict__ trunc_buf, float *__restrict__ logp_buf, float *__restrict__ last_val,
+                     float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes, int obs_mode) {
+    constexpr int kGroups = 2, kCols = 256, kHalf = 128, kEnvThreads = kGroups * 128;
+    extern __shared__ __align__(16) unsigned char smem[];
+    // [tables | pad to a 128-byte boundary | first-layer operands | A tiles (hi, lo per group) | logits [group][128][12]]
+    const int w_off = (int)((tc::smem_u32(smem) + (uint32_t)table_bytes + 127u) / 128u * 128u - tc::smem_u32(smem));
+    float *sw = reinterpret_cast<float *>(smem + w_off);
+    unsigned char *sA = smem + w_off + 4 * kTcBFloats * 4;
+    float *s_logit = reinterpret_cast<float *>(sA + kGroups * 2 * tc::kABytes);
+    __shared__ __align__(8) unsigned long long mb_rows[kGroups], mb_full_lo[kGroups], mb_full_hi[kGroups],
+        mb_cons_a[kGroups], mb_full_c[kGroups], mb_cons_c[kGroups], mb_logit[kGroups];
+    __shared__ uint32_t tmem_slot;
+    // the warp index through a shuffle: the compiler then knows that it — and every role branch below — is warp-uniform
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    for (int i = tid; i < 4 * kTcBFloats / 4; i += blockDim.x)            // [actor hi | actor lo | critic hi | critic lo]
+        reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(weights)[i];
+    if (tid == 0)
+        for (int g = 0; g < kGroups; ++g) {
+            tc::mbar_init(tc::smem_u32(&mb_rows[g]), 128);
+            tc::mbar_init(tc::smem_u32(&mb_full_lo[g]), 1);
+            tc::mbar_init(tc::smem_u32(&mb_full_hi[g]), 1);
+            tc::mbar_init(tc::smem_u32(&mb_cons_a[g]), 128);
+            tc::mbar_init(tc::smem_u32(&mb_full_c[g]), 1);
+            tc::mbar_init(tc::smem_u32(&mb_cons_c[g]), 128);
+            tc::mbar_init(tc::smem_u32(&mb_logit[g]), 128);
+        }
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);      // ends with __syncthreads()
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    const int n_forward = n_steps + (last_val ? 1 : 0);
+
+    if (warp == 2 * kEnvThreads / 32) {
+        // ===== MMA issuer (one lane): a polling state machine per group, so the groups never wait for each other =====
+        if ((tid & 31) == 0) {
+            const uint32_t sB = tc::smem_u32(sw);
+            const uint32_t idesc_half = tc::make_idesc_tf32(128, kHalf), idesc_full = tc::make_idesc_tf32(128, kCols);
+            int f[kGroups] = {0, 0}, stage[kGroups] = {0, 0};
+            int open = n_forward > 0 ? kGroups : 0;
+            auto issue = [&](uint32_t d, uint32_t ah, uint32_t bh, uint32_t idesc) {     // D = Ah*Bh + Al*Bh + Ah*Bl
+                const uint32_t al = ah + tc::kABytes, bl = bh + (uint32_t)(kTcBFloats * 4);
+#pragma unroll
+                for (int pr = 0; pr < 3; ++pr) {
+                    const uint32_t a0 = (pr == 1) ? al : ah, b0 = (pr == 2) ? bl : bh;
+#pragma unroll
+                    for (int ks = 0; ks < tc::kK / 8; ++ks)
+                        tc::mma_tf32(d, tc::make_smem_desc(a0 + ks * 2 * tc::kLBO), tc::make_smem_desc(b0 + ks * 2 * tc::kLBO),
+                                     idesc, (pr | ks) != 0);
+                }
+            };
+            for (long long spin = 0; open > 0; ++spin) {
+                if (spin > (1ll << 28)) __trap();                    // a protocol error must not hang the GPU box
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    if (f[g] == n_forward) continue;
+                    const uint32_t par = (uint32_t)(f[g] & 1);
+                    const uint32_t ah = tc::smem_u32(sA + g * 2 * tc::kABytes);
+                    const uint32_t d = tbase + (uint32_t)(g * kCols);
+                    if (stage[g] == 0) {
+                        // this pass's operand rows are written and the previous pass's critic columns are read out
+                        if (!tc::mbar_test(tc::smem_u32(&mb_rows[g]), par)) continue;
+                        if (f[g] > 0 && !tc::mbar_test(tc::smem_u32(&mb_cons_c[g]), par ^ 1u)) continue;
+                        tc::tc_fence_after();
+                        issue(d, ah, sB, idesc_half);                                        // actor units 0..127
+                        tc::mma_commit(tc::smem_u32(&mb_full_lo[g]));
+                        issue(d + kHalf, ah, sB + (uint32_t)((kHalf / 8) * tc::kSBO), idesc_half);   // actor units 128..255
+                        tc::mma_commit(tc::smem_u32(&mb_full_hi[g]));
+                        stage[g] = 1;
+                    } else {
+                        if (!tc::mbar_test(tc::smem_u32(&mb_cons_a[g]), par)) continue;      // the actor columns are read out
+                        tc::tc_fence_after();
+                        issue(d, ah, sB + (uint32_t)(2 * kTcBFloats * 4), idesc_full);       // critic, 256 units
+                        tc::mma_commit(tc::smem_u32(&mb_full_c[g]));
+                        stage[g] = 0;
+                        if (++f[g] == n_forward) --open;
+                    }
+                }
+            }
+        }
+    } else {
+        const bool policy = warp >= kEnvThreads / 32;
+        const int lt = policy ? tid - kEnvThreads : tid;
+        const int group = lt >> 7, row = lt & 127;
+        const int e_raw = blockIdx.x * kEnvThreads + lt;
+        const bool active = e_raw < n_envs;
+        const int e = active ? e_raw : n_envs - 1;           // idle threads shadow the last env (no stores)
+        float *my_logit = s_logit + (size_t)(group * 128 + row) * 12;
+        const uint32_t b_logit = tc::smem_u32(&mb_logit[group]), b_full_c = tc::smem_u32(&mb_full_c[group]);
+
+        if (policy) {
+            // ===== policy threads: the second layers of both nets for the environment on this TMEM lane =====
+            // The per-thread allocation of a 17-warp CTA is 96 registers (five warps on one scheduler's file); the
+            // policy threads need about 50, the environment threads want the 136 the plain step kernel has: hand them over.
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+            const uint32_t my_tmem = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(group * kCols);
+            const uint32_t b_full_lo = tc::smem_u32(&mb_full_lo[group]), b_full_hi = tc::smem_u32(&mb_full_hi[group]);
+            const uint32_t b_cons_a = tc::smem_u32(&mb_cons_a[group]), b_cons_c = tc::smem_u32(&mb_cons_c[group]);
+            const float *tail = c_policy_l2 + kL2Tail;
+            const float4 *w4 = reinterpret_cast<const float4 *>(c_policy_l2);          // 5 float4 per 2 hidden units
+            const float4 *wc = reinterpret_cast<const float4 *>(c_policy_l2 + kL2W2c);
+#ifdef CARENV_TC2_PROF
+            long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last_ = clock64();
+#endif
+            for (int f = 0; f < n_forward; ++f) {
+                const uint32_t par = (uint32_t)(f & 1);
+                float2 L[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) L[q] = make_float2(0.0f, 0.0f);
+                tc::mbar_wait(b_full_lo, par);
+                tc::tc_fence_after();
+                TC2_T(0);
+#pragma unroll 1
+                for (int c = 0; c < kCols; c += 16) {
+                    if (c == kHalf) { tc::mbar_wait(b_full_hi, par); tc::tc_fence_after(); }
+                    float v[16];
+                    tc::tmem_ld16(my_tmem + c, v);
+                    if (c + 16 == kCols) { tc::tc_fence_before(); tc::mbar_arrive(b_cons_a); }   // the actor columns are read out
+                    const float4 *p = w4 + (__shfl_sync(0xffffffffu, c, 0) >> 1) * 5;           // uniform address: LDCU
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float h0 = fmaxf(v[2 * i], 0.0f), h1 = fmaxf(v[2 * i + 1], 0.0f);
+                        const float4 a = p[5 * i], b = p[5 * i + 1], d = p[5 * i + 2], x = p[5 * i + 3], y = p[5 * i + 4];
+                        L[0] = __ffma2_rn(make_float2(h0, h0), make_float2(a.x, a.y), L[0]);
+                        L[1] = __ffma2_rn(make_float2(h0, h0), make_float2(a.z, a.w), L[1]);
+                        L[2] = __ffma2_rn(make_float2(h0, h0), make_float2(b.x, b.y), L[2]);
+                        L[3] = __ffma2_rn(make_float2(h0, h0), make_float2(b.z, b.w), L[3]);
+                        L[4] = __ffma2_rn(make_float2(h0, h0), make_float2(d.x, d.y), L[4]);
+                        L[0] = __ffma2_rn(make_float2(h1, h1), make_float2(d.z, d.w), L[0]);
+                        L[1] = __ffma2_rn(make_float2(h1, h1), make_float2(x.x, x.y), L[1]);
+                        L[2] = __ffma2_rn(make_float2(h1, h1), make_float2(x.z, x.w), L[2]);
+                        L[3] = __ffma2_rn(make_float2(h1, h1), make_float2(y.x, y.y), L[3]);
+                        L[4] = __ffma2_rn(make_float2(h1, h1), make_float2(y.z, y.w), L[4]);
+                    }
+                }
+                reinterpret_cast<float4 *>(my_logit)[0] = make_float4(L[0].x + tail[0], L[0].y + tail[1], L[1].x + tail[2], L[1].y + tail[3]);
+                reinterpret_cast<float4 *>(my_logit)[1] = make_float4(L[2].x + tail[4], L[2].y + tail[5], L[3].x + tail[6], L[3].y + tail[7]);
+                reinterpret_cast<float2 *>(my_logit)[4] = make_float2(L[4].x + tail[8], L[4].y + tail[9]);
+                tc::mbar_arrive(b_logit);                            // release: the logits are visible
+                TC2_T(1);
+                tc::mbar_wait(b_full_c, par);
+                tc::tc_fence_after();
+                TC2_T(2);
+                float2 V = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+                for (int c = 0; c < kCols; c += 16) {
+                    float v[16];
+                    tc::tmem_ld16(my_tmem + c, v);
+                    if (c + 16 == kCols) { tc::tc_fence_before(); tc::mbar_arrive(b_cons_c); }
+                    const float4 *pc = wc + (__shfl_sync(0xffffffffu, c, 0) >> 2);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 w = pc[i];
+                        V = __ffma2_rn(make_float2(fmaxf(v[4 * i], 0.0f), fmaxf(v[4 * i + 1], 0.0f)), make_float2(w.x, w.y), V);
+                        V = __ffma2_rn(make_float2(fmaxf(v[4 * i + 2], 0.0f), fmaxf(v[4 * i + 3], 0.0f)), make_float2(w.z, w.w), V);
+                    }
+                }
+                const float value = (V.x + V.y) + tail[10];
+                if (active) {
+                    if (f < n_steps) val_buf[(size_t)f * (size_t)n_envs + (size_t)e] = value;
+                    else last_val[e] = value;                        // bootstrap value of the final observation
+                }
+                TC2_T(3);
+            }
+#ifdef CARENV_TC2_PROF
+            if (blockIdx.x == 0 && lt == 0)
+                printf("tc2 policy thread cycles/step: wait_actor %lld actor %lld wait_critic %lld critic %lld\n",
+                       prof_[0] / n_forward, prof_[1] / n_forward, prof_[2] / n_forward, prof_[3] / n_forward);
+#endif
+        } else {
+            // ===== environment threads =====
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 136;\n");
+            unsigned char *myA = sA + group * 2 * tc::kABytes;   // hi tile, then lo tile
+            const uint32_t b_rows = tc::smem_u32(&mb_rows[group]);
+            EnvState s;
+            {
+                const double2 p = pos[e], v = vel[e];
+                const int4 q = ints[e];
+                s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
+                s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
+            }
+            float obs[kObsDim];
+            {
+                const float2 *src = reinterpret_cast<const float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+                for (int i = 0; i < kObsDim / 2; ++i) { const float2 v = src[i]; obs[2 * i] = v.x; obs[2 * i + 1] = v.y; }
+            }
+            float tc_ = cur_term[e], uc = cur_trunc[e];
+            const uint32_t gid = (uint32_t)(env_offset + e);
+
+            // operand row of pass f: obs | 1 | 0...  split into TF32 hi and lo
+            auto write_row = [&](int f) {
+                if (f > 0) tc::mbar_wait(b_full_c, (uint32_t)((f - 1) & 1));   // the previous pass's MMAs have read the tile
+#pragma unroll
+                for (int c = 0; c < tc::kKChunks; ++c) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = 4 * c + j;
+                        const float x = k < kObsDim ? obs[k < kObsDim ? k : 0] : (k == kObsDim ? 1.0f : 0.0f);
+                        hi[j] = tc::to_tf32(x);
+                        lo[j] = tc::to_tf32(x - hi[j]);
+                    }
+                    const int off = tc::operand_offset(row, 4 * c);
+                    *reinterpret_cast<float4 *>(myA + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4 *>(myA + tc::kABytes + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                tc::fence_async_smem();
+                tc::mbar_arrive(b_rows);
+            };
+
+#ifdef CARENV_TC2_PROF
+            long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last_ = clock64();
+#endif
+            for (int t = 0; t < n_steps; ++t) {
+                const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+                write_row(t);
+                TC2_T(0);
+                // Philox and the Buffer rows that do not depend on the action, while the tensor core and the policy thread work
+                const unsigned long long gs = step0 + (unsigned long long)t;
+                const uint32_t bits = philox_uniform_bits((uint32_t)seed, (uint32_t)(seed >> 32), gid, (uint32_t)gs,
+                                                          (uint32_t)(gs >> 32), 0x43415245u);
+                const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
+                if (active) {
+                    if (obs_mode == kObsPose) {
+                        store_pose(reinterpret_cast<PoseRec *>(obs_buf) + idx, s, obs[2], obs[3]);
+                    } else {
+                        float2 *dst = reinterpret_cast<float2 *>(obs_buf + idx * kObsDim);
+#pragma unroll
+                        for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+                    }
+                    term_buf[idx] = tc_;
+                    trunc_buf[idx] = uc;
+                    if (u_dbg) u_dbg[idx] = u;
+                }
+                TC2_T(1);
+                tc::mbar_wait(b_logit, (uint32_t)(t & 1));           // acquire: this step's logits
+                TC2_T(2);
+                PolicyOut po;
+                {
+                    const float4 p0 = reinterpret_cast<const float4 *>(my_logit)[0], p1 = reinterpret_cast<const float4 *>(my_logit)[1];
+                    const float2 p2 = reinterpret_cast<const float2 *>(my_logit)[4];
+                    po.logit[0] = p0.x; po.logit[1] = p0.y; po.logit[2] = p0.z; po.logit[3] = p0.w;
+                    po.logit[4] = p1.x; po.logit[5] = p1.y; po.logit[6] = p1.z; po.logit[7] = p1.w;
+                    po.logit[8] = p2.x; po.logit[9] = p2.y;
+                    po.value = 0.0f;
+                }
+                float logp, us;
+                const int a = sample_action(po, u, logp, us);
+                if (active) {
+                    act_buf[idx] = (float)a;
+                    logp_buf[idx] = logp;
+                }
+                TC2_T(3);
+                StepResult o;
+                env_step<U>(s, a, reward_scale, P, T, o, active ? stats : nullptr);
+                if (active) rew_buf[idx] = o.reward;
+#pragma unroll
+                for (int i = 0; i < kObsDim; ++i) obs[i] = o.obs[i];
+                tc_ = o.terminated ? 1.0f : 0.0f;
+                uc = o.truncated ? 1.0f : 0.0f;
+                TC2_T(4);
+            }
+#ifdef CARENV_TC2_PROF
+            if (blockIdx.x == 0 && lt == 0)
+                printf("tc2 env thread cycles/step: row %lld philox+stores %lld wait_logits %lld sample %lld env_step %lld\n",
+                       prof_[0] / n_steps, prof_[1] / n_steps, prof_[2] / n_steps, prof_[3] / n_steps, prof_[4] / n_steps);
+#endif
+            if (last_val) write_row(n_steps);                        // one more pass: the policy thread writes the bootstrap value
+            if (active) {
+                pos[e] = make_double2(s.px, s.py);
+                vel[e] = make_double2(s.vx, s.vy);
+                ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+                float2 *dst = reinterpret_cast<float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+                for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+                cur_term[e] = tc_;
+                cur_trunc[e] = uc;
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tbase);
+}

@@ -82,18 +82,21 @@ class FusedPPOUpdate:
         self._comm, self._comm_world = comm, world
         dist.barrier(group)              # every peer has mapped every buffer before anyone launches
 
-    def close(self):
+    def close(self, group=None):
+        """Collective when connected: a peer may still be reading this rank's exchange buffer (a rank's last update
+        completes when the peers' flags have arrived, not when they have finished reading), so every rank drains its
+        device and meets the others before anything is unmapped or freed."""
         if self._comm is not None:
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier(group)
             self.L.carenv_ppo_comm_destroy(self._comm)
             self._comm = None
 
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+    def __del__(self):                   # not collective: a communicator that was never closed is left to process exit
+        self._comm = None
 
-    def run_epoch(self, obs, idx, act, old_logp, adv, ret, world: int = 1, n_ctas: int = 0):
+    def run_epoch(self, obs, idx, act, old_logp, adv, ret, world: int = 1, n_ctas: int = 0, prof=None):
         """All ``idx.shape[0]`` minibatch updates (rows of ``idx`` [n_updates, batch] int64) in ONE launch: forward,
         loss, backward, gradient all-reduce over NVLink peer memory (``world`` > 1, after :meth:`connect`), clip,
         Adam, statistics into ``self.sums``.  Asynchronous; :meth:`check_epoch` reads the kernel's error word."""
@@ -105,6 +108,8 @@ class FusedPPOUpdate:
                 raise ValueError(f"{name} must be a contiguous float32 tensor on {self.device}")
         if obs.shape[-1] != 18:
             raise ValueError("obs must have 18 columns")
+        if prof is not None and (prof.dtype != torch.int64 or prof.numel() < 4 * idx.shape[0] or prof.device != self.device):
+            raise ValueError("prof must be an int64 device tensor of n_updates x 4 elements")
         if world > 1 and (self._comm is None or self._comm_world != world):
             raise _lib.CarEnvError("run_epoch(world > 1) needs connect() on every rank first")
         if self._epoch_ws is None:
@@ -116,7 +121,8 @@ class FusedPPOUpdate:
                                          self.ent_coef, _p(self.exp_avg), _p(self.exp_avg_sq), _p(self.lr),
                                          _p(self.step_count), self.betas[0], self.betas[1], self.eps,
                                          self.max_grad_norm, _p(self.sums), _p(self._epoch_ws), _p(self._sync),
-                                         self._comm if world > 1 else None, int(n_ctas), self._stream())
+                                         self._comm if world > 1 else None, int(n_ctas),
+                                         _p(prof) if prof is not None else None, self._stream())
         _lib.check(rc, "carenv_ppo_epoch")
 
     def check_epoch(self):

@@ -29,9 +29,10 @@ def test_pack_layout_matches_header_constants():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,tensor_cores", [(24, False), (1000, False), (24, 2), (1000, 2), (1000, 4), (2049, 4),
-                                            (1300, 2)])
+                                            (1300, 2), (24, 3), (1000, 3), (1300, 3)])
 def test_fused_rollout_matches_torch_policy_and_env_kernel(tracks_dir, n, tensor_cores):
-    """tensor_cores: False = CUDA-core kernel, 2 / 4 = tensor-core kernel with that many 128-env groups per CTA."""
+    """tensor_cores: False = CUDA-core kernel, 2 / 4 = tensor-core kernel with that many 128-env groups per CTA,
+    3 = two groups with a helper thread per environment (k_policy_rollout_tc2)."""
     dev = torch.device("cuda")
     path = os.path.join(tracks_dir, "big_track.json")
     T = 300
@@ -84,6 +85,8 @@ def test_fused_rollout_matches_torch_policy_and_env_kernel(tracks_dir, n, tensor
     env3 = ppo_car_b200.VecCarEnv(n - half, path, reward_scaling=0.1, float_flags=True)
     buf3 = ppo_car_b200.Buffer((18,), T, n - half, dev)
     o3 = env3.reset()[0].clone()
+    if tensor_cores:
+        env3.set_option("tc_tiles", int(tensor_cores))     # same kernel variant: same logit bits
     z = torch.zeros(n - half, device=dev)
     ppo_car_b200.fused_rollout(env3, packed, buf3, o3, z.clone(), z.clone(), seed=11, step0=5, env_offset=half)
     assert torch.equal(buf3.act_buf, buf.act_buf[:, half:]) and torch.equal(buf3.rew_buf, buf.rew_buf[:, half:])

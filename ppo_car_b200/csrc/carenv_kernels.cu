@@ -73,6 +73,7 @@ struct Handle {
     int block;                // tuning hook: threads per block of k_rollout (0 = chosen per launch, see rollout_block)
     int smem_pad;             // tuning hook: extra dynamic shared memory per block (limits resident blocks per SM)
     int tc_tiles;             // tuning hook: 128-env groups per CTA of k_policy_rollout_tc (0 = chosen per launch)
+    int tc_stagger;           // tuning hook: start delay of group 1 in k_policy_rollout_tc2, cycles (-1 = default)
     int pose_rows;            // fused rollout kernels: obs_buf holds 32-byte pose records instead of observations
     int warp_per_env;         // 0 = warp-per-environment kernel for small batches, 1 = always, -1 = never
     struct HostStep *hs;      // staging buffers / streams of carenv_step_host (allocated on first use)
@@ -794,7 +795,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->pose_rows = 0; h->warp_per_env = 0; h->hs = nullptr; h->d_den4 = nullptr; h->tab = 0; h->cur_rec = nullptr; h->cur_fobs = nullptr; h->host_ranges = 0;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->tc_stagger = -1; h->pose_rows = 0; h->warp_per_env = 0; h->hs = nullptr; h->d_den4 = nullptr; h->tab = 0; h->cur_rec = nullptr; h->cur_fobs = nullptr; h->host_ranges = 0;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -1215,6 +1216,7 @@ int carenv_set_option(void *handle, const char *name, int value) {
     if (std::string(name) == "host_ranges") { h->host_ranges = value < 0 ? 0 : value; return 0; }
     if (std::string(name) == "tab") { h->tab = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
     if (std::string(name) == "warp_per_env") { h->warp_per_env = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
+    if (std::string(name) == "tc_stagger") { h->tc_stagger = value; return 0; }
     if (std::string(name) == "tc_tiles") {
         if (value != 0 && (value < 2 || value > 4)) return fail(CARENV_E_INVAL, "tc_tiles must be 0, 2, 3 or 4");
         h->tc_tiles = value; return 0;

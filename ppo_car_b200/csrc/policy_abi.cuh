@@ -255,11 +255,8 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
     // 3 = two groups with a helper thread per environment (k_policy_rollout_tc2): the latency-bound shards
     int tiles = (n_envs + 511) / 512 >= sms ? 4 : 3;
     if (h->tc_tiles >= 2 && h->tc_tiles <= 4) tiles = h->tc_tiles;
-    // second-layer weights -> constant bank (k_policy_rollout_tc2 reads them as uniform operands)
-    CU(cudaMemcpyToSymbolAsync(c_policy_l2, packed_weights + kTcW2Off, sizeof(float) * (kTcWeightFloats - kTcW2Off), 0,
-                               cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     if (tiles == 3) {
-        const size_t smem2 = (size_t)table_bytes + 128 + (size_t)4 * kTcBFloats * 4 +      // first-layer operands only
+        const size_t smem2 = (size_t)table_bytes + 128 + (size_t)((kTcWeightFloats * 4 + 127) / 128 * 128) +
                              (size_t)2 * 2 * tc::kABytes + (size_t)2 * 128 * 12 * sizeof(float);
         if (smem2 > 227 * 1024) return fail(CARENV_E_TRACK, "track tables too large for the tensor-core rollout kernel");
         const int grid2 = (n_envs + 255) / 256;
@@ -271,7 +268,8 @@ int carenv_policy_rollout_tc(void *handle, const float *packed_weights, int n_en
                 h->host.P, h->dev, packed_weights, n_envs, n_steps, env_offset, seed, step0,
                 reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints), cur_obs,
                 cur_term, cur_trunc, reward_scale, obs_buf, act_buf, rew_buf, val_buf, term_buf, trunc_buf, logp_buf,
-                last_val, u_dbg, h->d_stats, table_bytes, h->pose_rows ? kObsPose : kObsFull);
+                last_val, u_dbg, h->d_stats, table_bytes, h->pose_rows ? kObsPose : kObsFull,
+                h->tc_stagger >= 0 ? h->tc_stagger : 0);
             CU(cudaGetLastError());
             return 0;
         };

@@ -436,22 +436,58 @@ k_policy_rollout_tc(const __grid_constant__ TrackParams P, const Tables G, const
 // ---- fused rollout, tensor cores, TWO threads per environment ---------------------------------------------------
 // k_policy_rollout_tc walks one dependent chain of ~6,900 instructions per environment and step (operand row ->
 // MMA -> 256 + 256 hidden units through the CUDA-core second layer -> sampling -> env step); with one 256-env CTA
-// per SM (shards of 32,768 envs, BASELINE config 5) that chain IS the step time, and its second layer also keeps
-// the shared-memory pipe busy for 10k of a step's 28k cycles (every warp streams the same 10 KB of weights: a
-// wavefront per 8 bytes).  Here every environment has an environment thread and a policy thread:
-//   environment thread   operand row, Buffer rows, Philox — then waits for the logits — sampling, env step
-//   policy thread        owns the environment's TMEM lane: ReLU + 256 -> 9 second layer with the weights as UNIFORM
-//                        operands from the constant bank (LDCU: no shared-memory traffic, no per-thread load),
-//                        logits to the environment thread through shared memory; then the whole critic and the
-//                        value row, off the critical path (it runs while the environment thread samples and steps)
-//   issuer lane          a polling state machine per 128-env group: actor MMAs as two N = 128 halves with their own
-//                        commit barriers (the policy threads start after the first half), the critic's N = 256
-//                        MMAs as soon as the actor columns are read out
-// Both nets sum their 256 products in the order of the other kernels: same logit, log-prob and value bits.
-// (The policy threads' loop is free of data-dependent control flow; that is what lets the compiler keep its
-// weight addresses in uniform registers — inside the environment threads' loop it falls back to per-thread LDC.)
-__constant__ __align__(16) float c_policy_l2[kTcWeightFloats - kTcW2Off];   // [unit][5] float2 | w2c[256] | tail[12]
-constexpr int kL2W2c = kTcW2cOff - kTcW2Off, kL2Tail = kTcTailOff - kTcW2Off;
+// per SM (shards of 32,768 envs, BASELINE config 5) that chain IS the step time.  Measured per step (cycle stamps,
+// benchmarks/tc2_phase_profile.py): env step 9.4k cycles, second layer 13k — of which 11k are the shared-memory
+// pipe delivering the broadcast weights (16 bytes x 32 lanes per LDS.128 = two return cycles; both 128-env groups
+// run their second layer at the same time because their MMAs complete together).  Here
+//   * every environment has an ENVIRONMENT thread (operand row, Buffer rows, Philox, hidden units 0..127 of the
+//     actor, sampling, env step) and a POLICY thread on the same TMEM lane (hidden units 128..255 of the actor —
+//     partial logits to the environment thread through shared memory — then the whole critic and the value row,
+//     off the critical path: it runs while the environment thread samples and steps);
+//   * the second-layer weight loads are software-pipelined by hand (second_layer_chunk16);
+//   * the issuer lane is a polling state machine per 128-env group (actor MMAs as two N = 128 halves with their
+//     own commit barriers, the critic's N = 256 MMAs as soon as the actor columns are read out), so the groups are
+//     independent (option tc_stagger delays group 1's start so that one group's second layer would run beside the
+//     other group's env step; measured: no effect on the step time, default 0).
+// The critic sums its 256 products in the order of the other kernels (same value bits); the logits are the sum of two
+// 128-unit partial chains, so they differ from the other kernels' in the last bits.
+// (Second-layer weights from the constant bank as uniform LDCU operands were measured too: 65 cycles per hidden
+// unit instead of 27 — the uniform load path delivers one 8-byte operand per ~12 cycles per scheduler.)
+// Two hidden units (h0, h1) of the actor through the 256 -> 9 layer: w = their ten weight pairs as five float4
+// ([unit][5] float2 layout), L[q] = logits (2q, 2q + 1).
+__device__ __forceinline__ void second_layer_pair(float h0, float h1, const float4 (&w)[5], float2 (&L)[5]) {
+    L[0] = __ffma2_rn(make_float2(h0, h0), make_float2(w[0].x, w[0].y), L[0]);
+    L[1] = __ffma2_rn(make_float2(h0, h0), make_float2(w[0].z, w[0].w), L[1]);
+    L[2] = __ffma2_rn(make_float2(h0, h0), make_float2(w[1].x, w[1].y), L[2]);
+    L[3] = __ffma2_rn(make_float2(h0, h0), make_float2(w[1].z, w[1].w), L[3]);
+    L[4] = __ffma2_rn(make_float2(h0, h0), make_float2(w[2].x, w[2].y), L[4]);
+    L[0] = __ffma2_rn(make_float2(h1, h1), make_float2(w[2].z, w[2].w), L[0]);
+    L[1] = __ffma2_rn(make_float2(h1, h1), make_float2(w[3].x, w[3].y), L[1]);
+    L[2] = __ffma2_rn(make_float2(h1, h1), make_float2(w[3].z, w[3].w), L[2]);
+    L[3] = __ffma2_rn(make_float2(h1, h1), make_float2(w[4].x, w[4].y), L[3]);
+    L[4] = __ffma2_rn(make_float2(h1, h1), make_float2(w[4].z, w[4].w), L[4]);
+}
+
+// Sixteen hidden units (TMEM columns already in v, weights at shared address a = [unit][5] float2).  Two hidden units
+// = five 16-byte weight loads + ten FFMA2.  Left to itself the compiler issues each load right before its first use
+// (one load in flight: 30 cycles of shared-memory latency per two FFMA2, 71 cycles per hidden unit measured); here
+// the loads of the NEXT pair are issued — as ordered volatile loads — before the current pair is consumed.
+__device__ __forceinline__ void second_layer_chunk16(uint32_t a, const float (&v)[16], float2 (&L)[5]) {
+    float4 wa[5], wb[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) wa[r] = tc::lds128(a + 16u * r);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+#pragma unroll
+        for (int r = 0; r < 5; ++r) wb[r] = tc::lds128(a + 80u * (i + 1) + 16u * r);
+        second_layer_pair(fmaxf(v[2 * i], 0.0f), fmaxf(v[2 * i + 1], 0.0f), wa, L);
+        if (i + 2 < 8) {
+#pragma unroll
+            for (int r = 0; r < 5; ++r) wa[r] = tc::lds128(a + 80u * (i + 2) + 16u * r);
+        }
+        second_layer_pair(fmaxf(v[2 * i + 2], 0.0f), fmaxf(v[2 * i + 3], 0.0f), wb, L);
+    }
+}
 
 #ifdef CARENV_TC2_PROF          // per-phase cycle counts of one environment / policy thread (kernel tuning builds only)
 #define TC2_T(i) do { const long long now_ = clock64(); prof_[i] += now_ - last_; last_ = now_; } while (0)
@@ -467,27 +503,28 @@ k_policy_rollout_tc2(const __grid_constant__ TrackParams P, const Tables G, cons
                      double reward_scale, float *__restrict__ obs_buf, float *__restrict__ act_buf,
                      float *__restrict__ rew_buf, float *__restrict__ val_buf, float *__restrict__ term_buf,
                      float *__restrict__ trunc_buf, float *__restrict__ logp_buf, float *__restrict__ last_val,
-                     float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes, int obs_mode) {
+                     float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes, int obs_mode,
+                     int stagger_cycles) {
     constexpr int kGroups = 2, kCols = 256, kHalf = 128, kEnvThreads = kGroups * 128;
     extern __shared__ __align__(16) unsigned char smem[];
-    // [tables | pad to a 128-byte boundary | first-layer operands | A tiles (hi, lo per group) | logits [group][128][12]]
+    // [tables | pad to a 128-byte boundary | weights | A tiles (hi, lo per group) | logits [group][128][12]]
     const int w_off = (int)((tc::smem_u32(smem) + (uint32_t)table_bytes + 127u) / 128u * 128u - tc::smem_u32(smem));
     float *sw = reinterpret_cast<float *>(smem + w_off);
-    unsigned char *sA = smem + w_off + 4 * kTcBFloats * 4;
+    unsigned char *sA = smem + w_off + ((kTcWeightFloats * 4 + 127) / 128 * 128);
     float *s_logit = reinterpret_cast<float *>(sA + kGroups * 2 * tc::kABytes);
     __shared__ __align__(8) unsigned long long mb_rows[kGroups], mb_full_lo[kGroups], mb_full_hi[kGroups],
         mb_cons_a[kGroups], mb_full_c[kGroups], mb_cons_c[kGroups], mb_logit[kGroups];
     __shared__ uint32_t tmem_slot;
     // the warp index through a shuffle: the compiler then knows that it — and every role branch below — is warp-uniform
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    for (int i = tid; i < 4 * kTcBFloats / 4; i += blockDim.x)            // [actor hi | actor lo | critic hi | critic lo]
+    for (int i = tid; i < kTcWeightFloats / 4; i += blockDim.x)
         reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(weights)[i];
     if (tid == 0)
         for (int g = 0; g < kGroups; ++g) {
             tc::mbar_init(tc::smem_u32(&mb_rows[g]), 128);
             tc::mbar_init(tc::smem_u32(&mb_full_lo[g]), 1);
             tc::mbar_init(tc::smem_u32(&mb_full_hi[g]), 1);
-            tc::mbar_init(tc::smem_u32(&mb_cons_a[g]), 128);
+            tc::mbar_init(tc::smem_u32(&mb_cons_a[g]), 256);
             tc::mbar_init(tc::smem_u32(&mb_full_c[g]), 1);
             tc::mbar_init(tc::smem_u32(&mb_cons_c[g]), 128);
             tc::mbar_init(tc::smem_u32(&mb_logit[g]), 128);
@@ -556,19 +593,19 @@ k_policy_rollout_tc2(const __grid_constant__ TrackParams P, const Tables G, cons
         const bool active = e_raw < n_envs;
         const int e = active ? e_raw : n_envs - 1;           // idle threads shadow the last env (no stores)
         float *my_logit = s_logit + (size_t)(group * 128 + row) * 12;
+        const uint32_t my_tmem = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(group * kCols);
+        const uint32_t w2s = tc::smem_u32(sw + kTcW2Off);            // [unit][5] float2 pairs
+        const uint32_t b_cons_a = tc::smem_u32(&mb_cons_a[group]);
         const uint32_t b_logit = tc::smem_u32(&mb_logit[group]), b_full_c = tc::smem_u32(&mb_full_c[group]);
 
         if (policy) {
             // ===== policy threads: the second layers of both nets for the environment on this TMEM lane =====
             // The per-thread allocation of a 17-warp CTA is 96 registers (five warps on one scheduler's file); the
-            // policy threads need about 50, the environment threads want the 136 the plain step kernel has: hand them over.
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
-            const uint32_t my_tmem = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(group * kCols);
-            const uint32_t b_full_lo = tc::smem_u32(&mb_full_lo[group]), b_full_hi = tc::smem_u32(&mb_full_hi[group]);
-            const uint32_t b_cons_a = tc::smem_u32(&mb_cons_a[group]), b_cons_c = tc::smem_u32(&mb_cons_c[group]);
-            const float *tail = c_policy_l2 + kL2Tail;
-            const float4 *w4 = reinterpret_cast<const float4 *>(c_policy_l2);          // 5 float4 per 2 hidden units
-            const float4 *wc = reinterpret_cast<const float4 *>(c_policy_l2 + kL2W2c);
+            // policy threads take 80 (two pairs of hidden units' weights in flight), the environment threads get 112.
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 80;\n");
+            const uint32_t b_full_hi = tc::smem_u32(&mb_full_hi[group]), b_cons_c = tc::smem_u32(&mb_cons_c[group]);
+            const float *tail = sw + kTcTailOff;
+            const float4 *wc = reinterpret_cast<const float4 *>(sw + kTcW2cOff);
 #ifdef CARENV_TC2_PROF
             long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last_ = clock64();
 #endif
@@ -577,36 +614,20 @@ k_policy_rollout_tc2(const __grid_constant__ TrackParams P, const Tables G, cons
                 float2 L[5];
 #pragma unroll
                 for (int q = 0; q < 5; ++q) L[q] = make_float2(0.0f, 0.0f);
-                tc::mbar_wait(b_full_lo, par);
+                tc::mbar_wait(b_full_hi, par);
                 tc::tc_fence_after();
                 TC2_T(0);
 #pragma unroll 1
-                for (int c = 0; c < kCols; c += 16) {
-                    if (c == kHalf) { tc::mbar_wait(b_full_hi, par); tc::tc_fence_after(); }
+                for (int c = kHalf; c < kCols; c += 16) {               // hidden units 128..255
                     float v[16];
                     tc::tmem_ld16(my_tmem + c, v);
-                    if (c + 16 == kCols) { tc::tc_fence_before(); tc::mbar_arrive(b_cons_a); }   // the actor columns are read out
-                    const float4 *p = w4 + (__shfl_sync(0xffffffffu, c, 0) >> 1) * 5;           // uniform address: LDCU
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float h0 = fmaxf(v[2 * i], 0.0f), h1 = fmaxf(v[2 * i + 1], 0.0f);
-                        const float4 a = p[5 * i], b = p[5 * i + 1], d = p[5 * i + 2], x = p[5 * i + 3], y = p[5 * i + 4];
-                        L[0] = __ffma2_rn(make_float2(h0, h0), make_float2(a.x, a.y), L[0]);
-                        L[1] = __ffma2_rn(make_float2(h0, h0), make_float2(a.z, a.w), L[1]);
-                        L[2] = __ffma2_rn(make_float2(h0, h0), make_float2(b.x, b.y), L[2]);
-                        L[3] = __ffma2_rn(make_float2(h0, h0), make_float2(b.z, b.w), L[3]);
-                        L[4] = __ffma2_rn(make_float2(h0, h0), make_float2(d.x, d.y), L[4]);
-                        L[0] = __ffma2_rn(make_float2(h1, h1), make_float2(d.z, d.w), L[0]);
-                        L[1] = __ffma2_rn(make_float2(h1, h1), make_float2(x.x, x.y), L[1]);
-                        L[2] = __ffma2_rn(make_float2(h1, h1), make_float2(x.z, x.w), L[2]);
-                        L[3] = __ffma2_rn(make_float2(h1, h1), make_float2(y.x, y.y), L[3]);
-                        L[4] = __ffma2_rn(make_float2(h1, h1), make_float2(y.z, y.w), L[4]);
-                    }
+                    if (c + 16 == kCols) { tc::tc_fence_before(); tc::mbar_arrive(b_cons_a); }   // this half is read out
+                    second_layer_chunk16(w2s + (uint32_t)c * 40u, v, L);
                 }
-                reinterpret_cast<float4 *>(my_logit)[0] = make_float4(L[0].x + tail[0], L[0].y + tail[1], L[1].x + tail[2], L[1].y + tail[3]);
-                reinterpret_cast<float4 *>(my_logit)[1] = make_float4(L[2].x + tail[4], L[2].y + tail[5], L[3].x + tail[6], L[3].y + tail[7]);
-                reinterpret_cast<float2 *>(my_logit)[4] = make_float2(L[4].x + tail[8], L[4].y + tail[9]);
-                tc::mbar_arrive(b_logit);                            // release: the logits are visible
+                reinterpret_cast<float4 *>(my_logit)[0] = make_float4(L[0].x, L[0].y, L[1].x, L[1].y);
+                reinterpret_cast<float4 *>(my_logit)[1] = make_float4(L[2].x, L[2].y, L[3].x, L[3].y);
+                reinterpret_cast<float2 *>(my_logit)[4] = L[4];
+                tc::mbar_arrive(b_logit);                            // release: the partial logits are visible
                 TC2_T(1);
                 tc::mbar_wait(b_full_c, par);
                 tc::tc_fence_after();
@@ -617,10 +638,9 @@ k_policy_rollout_tc2(const __grid_constant__ TrackParams P, const Tables G, cons
                     float v[16];
                     tc::tmem_ld16(my_tmem + c, v);
                     if (c + 16 == kCols) { tc::tc_fence_before(); tc::mbar_arrive(b_cons_c); }
-                    const float4 *pc = wc + (__shfl_sync(0xffffffffu, c, 0) >> 2);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 w = pc[i];
+                        const float4 w = wc[c / 4 + i];
                         V = __ffma2_rn(make_float2(fmaxf(v[4 * i], 0.0f), fmaxf(v[4 * i + 1], 0.0f)), make_float2(w.x, w.y), V);
                         V = __ffma2_rn(make_float2(fmaxf(v[4 * i + 2], 0.0f), fmaxf(v[4 * i + 3], 0.0f)), make_float2(w.z, w.w), V);
                     }
@@ -639,9 +659,10 @@ k_policy_rollout_tc2(const __grid_constant__ TrackParams P, const Tables G, cons
 #endif
         } else {
             // ===== environment threads =====
-            asm volatile("setmaxnreg.inc.sync.aligned.u32 136;\n");
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
             unsigned char *myA = sA + group * 2 * tc::kABytes;   // hi tile, then lo tile
-            const uint32_t b_rows = tc::smem_u32(&mb_rows[group]);
+            const uint32_t b_rows = tc::smem_u32(&mb_rows[group]), b_full_lo = tc::smem_u32(&mb_full_lo[group]);
+            const float *tail = sw + kTcTailOff;
             EnvState s;
             {
                 const double2 p = pos[e], v = vel[e];
@@ -679,6 +700,10 @@ k_policy_rollout_tc2(const __grid_constant__ TrackParams P, const Tables G, cons
                 tc::mbar_arrive(b_rows);
             };
 
+            if (group == 1 && stagger_cycles > 0) {                  // tuning hook (see the header)
+                const long long t0 = clock64();
+                while (clock64() - t0 < (long long)stagger_cycles) { }
+            }
 #ifdef CARENV_TC2_PROF
             long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last_ = clock64();
 #endif
@@ -704,15 +729,30 @@ k_policy_rollout_tc2(const __grid_constant__ TrackParams P, const Tables G, cons
                     if (u_dbg) u_dbg[idx] = u;
                 }
                 TC2_T(1);
-                tc::mbar_wait(b_logit, (uint32_t)(t & 1));           // acquire: this step's logits
+                float2 L[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) L[q] = make_float2(0.0f, 0.0f);
+                tc::mbar_wait(b_full_lo, (uint32_t)(t & 1));
+                tc::tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < kHalf; c += 16) {                   // hidden units 0..127
+                    float v[16];
+                    tc::tmem_ld16(my_tmem + c, v);
+                    if (c + 16 == kHalf) { tc::tc_fence_before(); tc::mbar_arrive(b_cons_a); }   // this half is read out
+                    second_layer_chunk16(w2s + (uint32_t)c * 40u, v, L);
+                }
+                TC2_T(5);
+                tc::mbar_wait(b_logit, (uint32_t)(t & 1));           // acquire: the policy thread's partial logits
                 TC2_T(2);
                 PolicyOut po;
                 {
                     const float4 p0 = reinterpret_cast<const float4 *>(my_logit)[0], p1 = reinterpret_cast<const float4 *>(my_logit)[1];
                     const float2 p2 = reinterpret_cast<const float2 *>(my_logit)[4];
-                    po.logit[0] = p0.x; po.logit[1] = p0.y; po.logit[2] = p0.z; po.logit[3] = p0.w;
-                    po.logit[4] = p1.x; po.logit[5] = p1.y; po.logit[6] = p1.z; po.logit[7] = p1.w;
-                    po.logit[8] = p2.x; po.logit[9] = p2.y;
+                    po.logit[0] = (L[0].x + p0.x) + tail[0]; po.logit[1] = (L[0].y + p0.y) + tail[1];
+                    po.logit[2] = (L[1].x + p0.z) + tail[2]; po.logit[3] = (L[1].y + p0.w) + tail[3];
+                    po.logit[4] = (L[2].x + p1.x) + tail[4]; po.logit[5] = (L[2].y + p1.y) + tail[5];
+                    po.logit[6] = (L[3].x + p1.z) + tail[6]; po.logit[7] = (L[3].y + p1.w) + tail[7];
+                    po.logit[8] = (L[4].x + p2.x) + tail[8]; po.logit[9] = (L[4].y + p2.y) + tail[9];
                     po.value = 0.0f;
                 }
                 float logp, us;
@@ -733,10 +773,15 @@ k_policy_rollout_tc2(const __grid_constant__ TrackParams P, const Tables G, cons
             }
 #ifdef CARENV_TC2_PROF
             if (blockIdx.x == 0 && lt == 0)
-                printf("tc2 env thread cycles/step: row %lld philox+stores %lld wait_logits %lld sample %lld env_step %lld\n",
-                       prof_[0] / n_steps, prof_[1] / n_steps, prof_[2] / n_steps, prof_[3] / n_steps, prof_[4] / n_steps);
+                printf("tc2 env thread cycles/step: row %lld philox+stores %lld wait+actor_lo %lld wait_partial %lld sample %lld env_step %lld\n",
+                       prof_[0] / n_steps, prof_[1] / n_steps, prof_[5] / n_steps, prof_[2] / n_steps, prof_[3] / n_steps, prof_[4] / n_steps);
 #endif
-            if (last_val) write_row(n_steps);                        // one more pass: the policy thread writes the bootstrap value
+            if (last_val) {                                          // one more pass: the policy thread writes the bootstrap value
+                write_row(n_steps);
+                tc::mbar_wait(b_full_lo, (uint32_t)(n_steps & 1));
+                tc::tc_fence_before();
+                tc::mbar_arrive(b_cons_a);
+            }
             if (active) {
                 pos[e] = make_double2(s.px, s.py);
                 vel[e] = make_double2(s.vx, s.vy);

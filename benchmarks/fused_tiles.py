@@ -27,7 +27,7 @@ for n, T in SIZES:
     term, trunc, lv = torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.empty(n, device=dev)
     res = {"n_envs": n, "steps_per_launch": T}
     for tag, packed, tiles in (("cuda_core", packed_cc, 0), ("tc_tiles2", packed_tc, 2), ("tc_tiles4", packed_tc, 4),
-                              ("tc_2groups_helpers", packed_tc, 3)):
+                              ("tc_2groups_helpers", packed_tc, 3), ("tc_shared_weight_loads", packed_tc, 5)):
         env.set_option("tc_tiles", tiles)
         for i in range(2):
             ppo_car_b200.fused_rollout(env, packed, buf, obs, term, trunc, seed=1, step0=i * T, last_val=lv)

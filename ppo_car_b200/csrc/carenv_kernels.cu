@@ -1218,7 +1218,7 @@ int carenv_set_option(void *handle, const char *name, int value) {
     if (std::string(name) == "warp_per_env") { h->warp_per_env = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
     if (std::string(name) == "tc_stagger") { h->tc_stagger = value; return 0; }
     if (std::string(name) == "tc_tiles") {
-        if (value != 0 && (value < 2 || value > 4)) return fail(CARENV_E_INVAL, "tc_tiles must be 0, 2, 3 or 4");
+        if (value != 0 && (value < 2 || value > 5)) return fail(CARENV_E_INVAL, "tc_tiles must be 0 or 2..5");
         h->tc_tiles = value; return 0;
     }
     if (std::string(name) == "smem_pad") {

@@ -798,3 +798,306 @@ k_policy_rollout_tc2(const __grid_constant__ TrackParams P, const Tables G, cons
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<512>(tbase);
 }
+
+// ---- fused rollout, tensor cores, every second-layer weight load shared by TWO environments --------------------
+// ncu of k_policy_rollout_tc2 (profiles/r2_policy_tc2_ncu.txt): the 256 -> 9 layer is bound by the shared-memory
+// RETURN path — a broadcast LDS.128 delivers 16 bytes to 32 lanes in two wavefronts, i.e. the weights of ONE packed
+// FFMA2 per cycle and SM, half of what the FMA pipes take — and all warps run that phase together because their
+// MMAs complete together (the pipe is ~100 % busy for 11k of a step's 29k cycles, 41 % on average).  Here every
+// weight load feeds two environments: the environment thread of lane r in group 0 runs hidden units 0..127 for
+// BOTH environments on TMEM lane r (group 0's and group 1's columns), its twin in group 1 runs units 128..255 for
+// both, and the two exchange the partial logits of each other's environment through shared memory.  The critic is
+// done by 128 critic threads, lane r for both environments of the lane as well, off the critical path.  One CTA =
+// 256 environment threads + 128 critic threads + the issuer warp (13 warps, 128 registers each at launch; the critic
+// warps hand 64 of theirs to the environment warps).  Logits = (units 0..127) + (units 128..255) + bias, the order
+// of k_policy_rollout_tc2: bit-identical to it; values bit-identical to every other kernel.
+__device__ __forceinline__ void second_layer_chunk16_x2(uint32_t a, const float (&va)[16], const float (&vb)[16],
+                                                        float2 (&La)[5], float2 (&Lb)[5]) {
+    float4 wa[5], wb[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) wa[r] = tc::lds128(a + 16u * r);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+#pragma unroll
+        for (int r = 0; r < 5; ++r) wb[r] = tc::lds128(a + 80u * (i + 1) + 16u * r);
+        second_layer_pair(fmaxf(va[2 * i], 0.0f), fmaxf(va[2 * i + 1], 0.0f), wa, La);
+        second_layer_pair(fmaxf(vb[2 * i], 0.0f), fmaxf(vb[2 * i + 1], 0.0f), wa, Lb);
+        if (i + 2 < 8) {
+#pragma unroll
+            for (int r = 0; r < 5; ++r) wa[r] = tc::lds128(a + 80u * (i + 2) + 16u * r);
+        }
+        second_layer_pair(fmaxf(va[2 * i + 2], 0.0f), fmaxf(va[2 * i + 3], 0.0f), wb, La);
+        second_layer_pair(fmaxf(vb[2 * i + 2], 0.0f), fmaxf(vb[2 * i + 3], 0.0f), wb, Lb);
+    }
+}
+
+template <int U, bool TAB>
+__global__ void __launch_bounds__(256 + 128 + 32, 1)
+k_policy_rollout_tc3(const __grid_constant__ TrackParams P, const Tables G, const float *__restrict__ weights,
+                     int n_envs, int n_steps, int env_offset, unsigned long long seed, unsigned long long step0,
+                     double2 *__restrict__ pos, double2 *__restrict__ vel, int4 *__restrict__ ints,
+                     float *__restrict__ cur_obs, float *__restrict__ cur_term, float *__restrict__ cur_trunc,
+                     double reward_scale, float *__restrict__ obs_buf, float *__restrict__ act_buf,
+                     float *__restrict__ rew_buf, float *__restrict__ val_buf, float *__restrict__ term_buf,
+                     float *__restrict__ trunc_buf, float *__restrict__ logp_buf, float *__restrict__ last_val,
+                     float *__restrict__ u_dbg, unsigned long long *stats, int table_bytes, int obs_mode,
+                     const float4 *__restrict__ den4, int n_pairs, int row_f4) {
+    constexpr int kGroups = 2, kCols = 256, kHalf = 128, kEnvThreads = kGroups * 128, kCriticThreads = 128;
+    extern __shared__ __align__(16) unsigned char smem[];
+    // [tables | pad to a 128-byte boundary | weights | A tiles (hi, lo per group) | exchanged partial logits [group][128][12]
+    //  | TAB: the denominator table of k_rollout_tab, ONE copy whose rows are skewed by 16 bytes (row_f4 is odd in
+    //    16-byte units): threads of a quarter warp with different headings mostly hit different bank groups (about
+    //    2.6 instead of 1 wavefront per quarter — there is no room for the eight conflict-free copies) — this replaces
+    //    the 144 x (DMUL + DFMA + F2F) per env-step that the arithmetic kernels spend on the same values]
+    const int w_off = (int)((tc::smem_u32(smem) + (uint32_t)table_bytes + 127u) / 128u * 128u - tc::smem_u32(smem));
+    float *sw = reinterpret_cast<float *>(smem + w_off);
+    unsigned char *sA = smem + w_off + ((kTcWeightFloats * 4 + 127) / 128 * 128);
+    float *s_xchg = reinterpret_cast<float *>(sA + kGroups * 2 * tc::kABytes);
+    float4 *s_tab = reinterpret_cast<float4 *>(s_xchg + kGroups * 128 * 12);
+    if (TAB)
+        for (int i = threadIdx.x; i < kHeadings * n_pairs; i += blockDim.x) {
+            const int k = i / n_pairs, jp = i - k * n_pairs;
+            s_tab[k * row_f4 + jp] = den4[i];
+        }
+    const TabView tv{s_tab, row_f4};
+    __shared__ __align__(8) unsigned long long mb_rows, mb_full_lo, mb_full_hi, mb_cons_a, mb_full_c, mb_cons_c, mb_xchg;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    for (int i = tid; i < kTcWeightFloats / 4; i += blockDim.x)
+        reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(weights)[i];
+    if (tid == 0) {
+        tc::mbar_init(tc::smem_u32(&mb_rows), kEnvThreads);
+        tc::mbar_init(tc::smem_u32(&mb_full_lo), 1);
+        tc::mbar_init(tc::smem_u32(&mb_full_hi), 1);
+        tc::mbar_init(tc::smem_u32(&mb_cons_a), kEnvThreads);
+        tc::mbar_init(tc::smem_u32(&mb_full_c), 1);
+        tc::mbar_init(tc::smem_u32(&mb_cons_c), kCriticThreads);
+        tc::mbar_init(tc::smem_u32(&mb_xchg), kEnvThreads);
+    }
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);      // ends with __syncthreads()
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    const int n_forward = n_steps + (last_val ? 1 : 0);
+    const uint32_t b_rows = tc::smem_u32(&mb_rows), b_full_lo = tc::smem_u32(&mb_full_lo), b_full_hi = tc::smem_u32(&mb_full_hi);
+    const uint32_t b_cons_a = tc::smem_u32(&mb_cons_a), b_full_c = tc::smem_u32(&mb_full_c), b_cons_c = tc::smem_u32(&mb_cons_c);
+    const uint32_t b_xchg = tc::smem_u32(&mb_xchg);
+
+    if (warp == (kEnvThreads + kCriticThreads) / 32) {
+        // ===== MMA issuer (one lane); both groups advance together (their threads share the weight loads) =====
+        if ((tid & 31) == 0) {
+            const uint32_t sB = tc::smem_u32(sw);
+            const uint32_t idesc_half = tc::make_idesc_tf32(128, kHalf), idesc_full = tc::make_idesc_tf32(128, kCols);
+            auto issue = [&](uint32_t d, uint32_t ah, uint32_t bh, uint32_t idesc) {     // D = Ah*Bh + Al*Bh + Ah*Bl
+                const uint32_t al = ah + tc::kABytes, bl = bh + (uint32_t)(kTcBFloats * 4);
+#pragma unroll
+                for (int pr = 0; pr < 3; ++pr) {
+                    const uint32_t a0 = (pr == 1) ? al : ah, b0 = (pr == 2) ? bl : bh;
+#pragma unroll
+                    for (int ks = 0; ks < tc::kK / 8; ++ks)
+                        tc::mma_tf32(d, tc::make_smem_desc(a0 + ks * 2 * tc::kLBO), tc::make_smem_desc(b0 + ks * 2 * tc::kLBO),
+                                     idesc, (pr | ks) != 0);
+                }
+            };
+            const uint32_t a0 = tc::smem_u32(sA), a1 = a0 + 2 * tc::kABytes;
+            const uint32_t b_hi_half = sB + (uint32_t)((kHalf / 8) * tc::kSBO), b_critic = sB + (uint32_t)(2 * kTcBFloats * 4);
+            for (int f = 0; f < n_forward; ++f) {
+                const uint32_t par = (uint32_t)(f & 1);
+                tc::mbar_wait(b_rows, par);                          // this pass's operand rows are written
+                if (f > 0) tc::mbar_wait(b_cons_c, par ^ 1u);        // the previous pass's critic columns are read out
+                tc::tc_fence_after();
+                issue(tbase, a0, sB, idesc_half);                    // actor units 0..127, both groups
+                issue(tbase + kCols, a1, sB, idesc_half);
+                tc::mma_commit(b_full_lo);
+                issue(tbase + kHalf, a0, b_hi_half, idesc_half);     // actor units 128..255, both groups
+                issue(tbase + kCols + kHalf, a1, b_hi_half, idesc_half);
+                tc::mma_commit(b_full_hi);
+                tc::mbar_wait(b_cons_a, par);                        // the actor columns are read out
+                tc::tc_fence_after();
+                issue(tbase, a0, b_critic, idesc_full);              // critic, 256 units, both groups
+                issue(tbase + kCols, a1, b_critic, idesc_full);
+                tc::mma_commit(b_full_c);
+            }
+        }
+    } else if (warp >= kEnvThreads / 32) {
+        // ===== critic threads: lane r's two environments, every weight load used twice =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
+        const int row = tid - kEnvThreads;
+        const uint32_t lane_tmem = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        const int ea_raw = blockIdx.x * kEnvThreads + row, eb_raw = ea_raw + 128;
+        const float4 *wc = reinterpret_cast<const float4 *>(sw + kTcW2cOff);
+        const float bias = sw[kTcTailOff + 10];
+        for (int f = 0; f < n_forward; ++f) {
+            tc::mbar_wait(b_full_c, (uint32_t)(f & 1));
+            tc::tc_fence_after();
+            float2 Va = make_float2(0.0f, 0.0f), Vb = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+            for (int c = 0; c < kCols; c += 16) {
+                float va[16], vb[16];
+                tc::tmem_ld16(lane_tmem + c, va);
+                tc::tmem_ld16(lane_tmem + kCols + c, vb);
+                if (c + 16 == kCols) { tc::tc_fence_before(); tc::mbar_arrive(b_cons_c); }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 w = wc[c / 4 + i];
+                    Va = __ffma2_rn(make_float2(fmaxf(va[4 * i], 0.0f), fmaxf(va[4 * i + 1], 0.0f)), make_float2(w.x, w.y), Va);
+                    Vb = __ffma2_rn(make_float2(fmaxf(vb[4 * i], 0.0f), fmaxf(vb[4 * i + 1], 0.0f)), make_float2(w.x, w.y), Vb);
+                    Va = __ffma2_rn(make_float2(fmaxf(va[4 * i + 2], 0.0f), fmaxf(va[4 * i + 3], 0.0f)), make_float2(w.z, w.w), Va);
+                    Vb = __ffma2_rn(make_float2(fmaxf(vb[4 * i + 2], 0.0f), fmaxf(vb[4 * i + 3], 0.0f)), make_float2(w.z, w.w), Vb);
+                }
+            }
+            const float value_a = (Va.x + Va.y) + bias, value_b = (Vb.x + Vb.y) + bias;
+            if (f < n_steps) {
+                if (ea_raw < n_envs) val_buf[(size_t)f * (size_t)n_envs + (size_t)ea_raw] = value_a;
+                if (eb_raw < n_envs) val_buf[(size_t)f * (size_t)n_envs + (size_t)eb_raw] = value_b;
+            } else {                                                 // bootstrap values of the final observations
+                if (ea_raw < n_envs) last_val[ea_raw] = value_a;
+                if (eb_raw < n_envs) last_val[eb_raw] = value_b;
+            }
+        }
+    } else {
+        // ===== environment threads =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 160;\n");
+        const int group = tid >> 7, row = tid & 127;
+        const int e_raw = blockIdx.x * kEnvThreads + tid;
+        const bool active = e_raw < n_envs;
+        const int e = active ? e_raw : n_envs - 1;           // idle threads shadow the last env (no stores)
+        const uint32_t lane_tmem = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t w2s = tc::smem_u32(sw + kTcW2Off) + (uint32_t)(group * kHalf) * 40u;   // this thread's 128 hidden units
+        const uint32_t b_full_mine = group == 0 ? b_full_lo : b_full_hi;
+        float *xchg_out = s_xchg + (size_t)((1 - group) * 128 + row) * 12;    // partial logits of the OTHER group's lane-r env
+        const float *xchg_in = s_xchg + (size_t)(group * 128 + row) * 12;
+        unsigned char *myA = sA + group * 2 * tc::kABytes;   // hi tile, then lo tile
+        const float *tail = sw + kTcTailOff;
+        EnvState s;
+        {
+            const double2 p = pos[e], v = vel[e];
+            const int4 q = ints[e];
+            s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
+            s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
+        }
+        float obs[kObsDim];
+        {
+            const float2 *src = reinterpret_cast<const float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+            for (int i = 0; i < kObsDim / 2; ++i) { const float2 v = src[i]; obs[2 * i] = v.x; obs[2 * i + 1] = v.y; }
+        }
+        float tc_ = cur_term[e], uc = cur_trunc[e];
+        const uint32_t gid = (uint32_t)(env_offset + e);
+
+        auto write_row = [&](int f) {
+            if (f > 0) tc::mbar_wait(b_full_c, (uint32_t)((f - 1) & 1));   // the previous pass's MMAs have read the tile
+#pragma unroll
+            for (int c = 0; c < tc::kKChunks; ++c) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 4 * c + j;
+                    const float x = k < kObsDim ? obs[k < kObsDim ? k : 0] : (k == kObsDim ? 1.0f : 0.0f);
+                    hi[j] = tc::to_tf32(x);
+                    lo[j] = tc::to_tf32(x - hi[j]);
+                }
+                const int off = tc::operand_offset(row, 4 * c);
+                *reinterpret_cast<float4 *>(myA + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(myA + tc::kABytes + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            tc::fence_async_smem();
+            tc::mbar_arrive(b_rows);
+        };
+
+        for (int t = 0; t < n_steps; ++t) {
+            const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+            const uint32_t par = (uint32_t)(t & 1);
+            write_row(t);
+            const unsigned long long gs = step0 + (unsigned long long)t;
+            const uint32_t bits = philox_uniform_bits((uint32_t)seed, (uint32_t)(seed >> 32), gid, (uint32_t)gs,
+                                                      (uint32_t)(gs >> 32), 0x43415245u);
+            const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
+            if (active) {
+                if (obs_mode == kObsPose) {
+                    store_pose(reinterpret_cast<PoseRec *>(obs_buf) + idx, s, obs[2], obs[3]);
+                } else {
+                    float2 *dst = reinterpret_cast<float2 *>(obs_buf + idx * kObsDim);
+#pragma unroll
+                    for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+                }
+                term_buf[idx] = tc_;
+                trunc_buf[idx] = uc;
+                if (u_dbg) u_dbg[idx] = u;
+            }
+            // my 128 hidden units for the two environments of TMEM lane r (a = group 0's, b = group 1's)
+            float2 La[5], Lb[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) { La[q] = make_float2(0.0f, 0.0f); Lb[q] = make_float2(0.0f, 0.0f); }
+            tc::mbar_wait(b_full_mine, par);
+            tc::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < kHalf; c += 16) {
+                float va[16], vb[16];
+                tc::tmem_ld16(lane_tmem + group * kHalf + c, va);
+                tc::tmem_ld16(lane_tmem + kCols + group * kHalf + c, vb);
+                if (c + 16 == kHalf) { tc::tc_fence_before(); tc::mbar_arrive(b_cons_a); }   // my columns are read out
+                second_layer_chunk16_x2(w2s + (uint32_t)c * 40u, va, vb, La, Lb);
+            }
+            {   // hand the other environment's partial logits to its thread, take mine
+                const float2 *o = group == 0 ? Lb : La;
+                reinterpret_cast<float4 *>(xchg_out)[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+                reinterpret_cast<float4 *>(xchg_out)[1] = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+                reinterpret_cast<float2 *>(xchg_out)[4] = o[4];
+            }
+            tc::mbar_arrive(b_xchg);
+            tc::mbar_wait(b_xchg, par);
+            PolicyOut po;
+            {
+                const float2 *m = group == 0 ? La : Lb;
+                const float4 p0 = reinterpret_cast<const float4 *>(xchg_in)[0], p1 = reinterpret_cast<const float4 *>(xchg_in)[1];
+                const float2 p2 = reinterpret_cast<const float2 *>(xchg_in)[4];
+                const float r[10] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y};
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    // (units 0..127) + (units 128..255): the same operands in the same order on both threads
+                    const float lo0 = group == 0 ? m[q].x : r[2 * q], hi0 = group == 0 ? r[2 * q] : m[q].x;
+                    const float lo1 = group == 0 ? m[q].y : r[2 * q + 1], hi1 = group == 0 ? r[2 * q + 1] : m[q].y;
+                    po.logit[2 * q] = (lo0 + hi0) + tail[2 * q];
+                    po.logit[2 * q + 1] = (lo1 + hi1) + tail[2 * q + 1];
+                }
+                po.value = 0.0f;
+            }
+            float logp, us;
+            const int a = sample_action(po, u, logp, us);
+            if (active) {
+                act_buf[idx] = (float)a;
+                logp_buf[idx] = logp;
+            }
+            StepResult o;
+            env_step<U, TAB>(s, a, reward_scale, P, T, o, active ? stats : nullptr, nullptr, TAB ? &tv : nullptr);
+            if (active) rew_buf[idx] = o.reward;
+#pragma unroll
+            for (int i = 0; i < kObsDim; ++i) obs[i] = o.obs[i];
+            tc_ = o.terminated ? 1.0f : 0.0f;
+            uc = o.truncated ? 1.0f : 0.0f;
+        }
+        if (last_val) {                                          // one more pass: the critic threads write the bootstrap values
+            write_row(n_steps);
+            tc::mbar_wait(b_full_mine, (uint32_t)(n_steps & 1));
+            tc::tc_fence_before();
+            tc::mbar_arrive(b_cons_a);
+        }
+        if (active) {
+            pos[e] = make_double2(s.px, s.py);
+            vel[e] = make_double2(s.vx, s.vy);
+            ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+            float2 *dst = reinterpret_cast<float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+            for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+            cur_term[e] = tc_;
+            cur_trunc[e] = uc;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tbase);
+}

@@ -11,10 +11,15 @@
 //   k_observe   observations recomputed from 32-byte pose records (compact rollout storage).
 //   k_reset     CarEnv.reset for every environment.
 //   k_gae       Buffer.calculate_advantages as a reverse scan, one thread per environment column.
-//   k_policy_rollout / k_policy_rollout_tc   policy forward + sampling + env step + Buffer rows in one launch
-//               (CUDA cores / tcgen05 tensor cores, csrc/policy_core.cuh, csrc/tc_mlp.cuh); k_pack_policy packs the
-//               network parameters for them.
-//   k_ppo_*     fused PPO minibatch update (csrc/ppo_update.cuh).
+//   k_rollout_tab   launches of 4,096 environments or more: the same step with the denominators cross(e, d) read
+//               from a per-track shared-memory table (8 skewed, conflict-free copies), one 512-thread CTA per SM.
+//   k_rollout_multi / k_reset_multi / k_render   a track id per environment in one launch; headless rgb_array frames.
+//   csrc/policy_rollout.cuh (included below)   k_policy_rollout / k_policy_rollout_tc / _tc2 / _tc3: policy forward +
+//               sampling + env step + Buffer rows in one launch (CUDA cores / tcgen05 tensor cores, policy_core.cuh,
+//               tc_mlp.cuh); k_pack_policy packs the network parameters for them.
+//   csrc/ppo_update.cuh, csrc/ppo_epoch.cuh   fused PPO minibatch update in three launches / all updates of an epoch
+//               in one persistent launch with the gradient all-reduce over NVLink peer memory inside the kernel.
+//   csrc/policy_abi.cuh (included below)   the C-ABI entry points of the policy / PPO kernels.
 //   carenv_step_host   the host-buffer step: sub-range pipeline of narrowing, H2D, kernel and D2H copies.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --shared -Xcompiler -fPIC

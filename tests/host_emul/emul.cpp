@@ -54,3 +54,12 @@ extern "C" int emul_rollout(const double *walls, int n_walls, const double *gate
     }
     return 0;
 }
+
+// The 72-entry float64 heading table (cos, sin of initial_angle + 5k degrees) exactly as the product builds it.
+extern "C" int emul_heading_table(double angle, double *cos_sin_out /* [72][2] */) {
+    const double walls[4] = {0.0, 0.0, 1.0, 0.0}, gates[4] = {0.0, 1.0, 1.0, 1.0};
+    HostTrack H;
+    if (build_host_track(walls, 1, gates, 1, 0.5, 0.5, angle, H) != 0) return -1;
+    for (int k = 0; k < kHeadings; ++k) { cos_sin_out[2 * k] = H.trig64[k].x; cos_sin_out[2 * k + 1] = H.trig64[k].y; }
+    return 0;
+}

@@ -206,3 +206,36 @@ def test_next_gate_only_test_equals_the_full_ordered_gate_scan(tracks_dir, name)
                time_passed=e["info"][..., 1], next_gate_index=e["info"][..., 2])
     assert_trajectory_matches(got, ref, what=f"{name}, full gate scan")
     assert (e["info"][..., 3] & 1).sum() > 2000                # gate events
+
+
+def test_heading_table_equals_numpy_trigonometry(tracks_dir):
+    """The kernels take cos / sin of the heading from a 72-entry table built with libm; the reference evaluates
+    np.cos(np.radians(rotation)) (lib/car_env.py:430, 155-160) and the C oracle shares libm with the table — so this is
+    the one place where kernel and oracle could jointly differ from the reference.  Checked directly: for the initial
+    angles of the shipped tracks (and a few odd ones) the table is bit-identical to numpy on the wrapped angle, and
+    within 4e-15 of numpy on the UNWRAPPED angles the reference reaches after turning (rotation is never wrapped
+    there: the documented deviation)."""
+    import ctypes as C
+    import json
+
+    from tests.emul_util import lib
+
+    L = lib()
+    angles = {0.0, 90.0, 180.0, 270.0, 33.0, 12.5}
+    for name in ("big_track.json", "track.json"):
+        with open(os.path.join(tracks_dir, name)) as fh:
+            angles.add(float(json.load(fh)["initial_angle"]))
+    for ang in sorted(angles):
+        tab = np.zeros((72, 2))
+        assert L.emul_heading_table(C.c_double(ang), tab.ctypes.data_as(C.c_void_p)) == 0
+        k = np.arange(72)
+        rad = np.radians(ang + 5.0 * k)
+        assert np.array_equal(tab[:, 0], np.cos(rad)) and np.array_equal(tab[:, 1], np.sin(rad)), ang
+        # unwrapped: two full turns either way, accumulated by +-5.0 in float64 exactly as Car.move_car does
+        for turns in (-2, -1, 1, 2):
+            rot = ang + 5.0 * (k + 72 * turns)
+            for col, fn in ((0, np.cos), (1, np.sin)):
+                ref = fn(np.radians(rot))
+                err = np.abs(tab[:, col] - ref)
+                # the argument itself is only known to half a unit in the last place of ~13 rad: a few 1e-15
+                assert err.max() <= 4.0e-15, (ang, turns, err.max())

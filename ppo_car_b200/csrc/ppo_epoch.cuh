@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(kEpochThreads, 1) k_ppo_epoch(const EpochArgs 
     __shared__ float s_part[SMAX][3];                    // per-sample policy loss, entropy, value loss
     __shared__ float s_red8[8];
     __shared__ float4 s_fold[8];
+    __shared__ float s_bias[2];
     __shared__ float s_b2[kZ], s_b2m[kZ], s_b2v[kZ];     // second-layer biases (b2a[0..8], b2c) and their moments
     __shared__ int s_flag;
 
@@ -482,11 +483,14 @@ __global__ void __launch_bounds__(kEpochThreads, 1) k_ppo_epoch(const EpochArgs 
                 __stcg(reinterpret_cast<float4 *>(A.stat) + par * kMaxCtas + c, make_float4(ss, p0, p1, p2));
             }
         }
-        // bias corrections of this step while the barrier is pending
-        const int t_step = step0 + u + 1;
-        const float bc1 = 1.0f - powf(A.beta1, (float)t_step), bc2 = 1.0f - powf(A.beta2, (float)t_step);
-        const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+        // bias corrections of this step, by one thread while the barrier is pending (powf is ~150 instructions)
+        if (j == 64) {
+            const int t_step = step0 + u + 1;
+            const float bc1 = 1.0f - powf(A.beta1, (float)t_step), bc2 = 1.0f - powf(A.beta2, (float)t_step);
+            s_bias[0] = lr / bc1; s_bias[1] = rsqrtf(bc2);
+        }
         if (grid_barrier(A.bar, bar_target, A.err, &s_flag)) return;
+        const float step_size = s_bias[0], inv_sqrt_bc2 = s_bias[1];
         if (stamp) A.prof[4 * u + 2] = global_ns();
 
         // ---- phase C: clip_grad_norm_ + Adam on this CTA's copy of every parameter, statistics

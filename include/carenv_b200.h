@@ -256,6 +256,18 @@ int carenv_ppo_adam(float *w1_actor, float *b1_actor, float *w2_actor, float *b2
                     double eps, double max_grad_norm, const float *scratch, int batch, double vf_coef,
                     double ent_coef, float *sums4, void *stream);
 
+/* carenv_policy_rollout for SMALL batches (the reference's own training shape is 24 environments): one warp per
+ * environment — lane = wall segment in the env step, lane = 16 hidden units in the policy — on tracks with at most 32
+ * wall segments.  The network parameters are passed in nn.Linear layout (lib/model.py:10-26: weight [out][in], bias),
+ * no packing; other arguments as carenv_policy_rollout.  Same random stream; float32 CUDA cores. */
+int carenv_policy_rollout_warp(void *handle, const float *w1_actor, const float *b1_actor, const float *w2_actor,
+                               const float *b2_actor, const float *w1_critic, const float *b1_critic,
+                               const float *w2_critic, const float *b2_critic, int n_envs, int n_steps, int env_offset,
+                               unsigned long long seed, unsigned long long step0, double *pos, double *vel,
+                               int32_t *ints, float *cur_obs, float *cur_term, float *cur_trunc, double reward_scale,
+                               float *obs_buf, float *act_buf, float *rew_buf, float *val_buf, float *term_buf,
+                               float *trunc_buf, float *logp_buf, float *last_val, float *u_dbg, void *stream);
+
 /* All minibatch updates of one PPO epoch in ONE persistent cooperative launch (csrc/ppo_epoch.cuh; replaces the
  * loops of train.py:223-261 — `for _ in range(train_iters): for start in range(0, n_steps, batch_size): ...` — and,
  * with several GPUs, the gradient all-reduce between backward and optimizer.step()).

@@ -9,8 +9,8 @@ from ._lib import CarEnvError, build
 from .buffer import Buffer, gae_reverse_scan
 from .track import Track, builtin_track, load_track, validate_track
 from .vec_env import MultiTrackVecEnv, VecCarEnv
-from .policy import fused_rollout, pack_policy_weights, pack_policy_weights_tc
+from .policy import fused_rollout, fused_rollout_warp, pack_policy_weights, pack_policy_weights_tc
 from .ppo_update import FusedPPOUpdate
 
 __all__ = ["VecCarEnv", "MultiTrackVecEnv", "validate_track", "Buffer", "gae_reverse_scan", "load_track", "builtin_track", "Track", "build", "CarEnvError",
-           "fused_rollout", "pack_policy_weights", "pack_policy_weights_tc", "FusedPPOUpdate"]
+           "fused_rollout", "fused_rollout_warp", "pack_policy_weights", "pack_policy_weights_tc", "FusedPPOUpdate"]

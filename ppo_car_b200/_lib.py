@@ -107,6 +107,9 @@ def lib():
     L.carenv_policy_weights_floats.restype = i32
     L.carenv_policy_rollout.argtypes = [vp, vp, i32, i32, i32, C.c_ulonglong, C.c_ulonglong, vp, vp, vp, vp, vp, vp,
                                         f64] + [vp] * 10
+    L.carenv_policy_rollout_warp.argtypes = [vp] + [vp] * 8 + [i32, i32, i32, C.c_ulonglong, C.c_ulonglong, vp, vp, vp, vp, vp,
+                                                            vp, f64] + [vp] * 10
+    L.carenv_policy_rollout_warp.restype = i32
     L.carenv_policy_weights_floats_tc.restype = i32
     L.carenv_policy_rollout_tc.argtypes = L.carenv_policy_rollout.argtypes
     for name in ("carenv_create", "carenv_destroy", "carenv_reset_obs", "carenv_reset", "carenv_step",

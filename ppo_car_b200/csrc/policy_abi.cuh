@@ -218,6 +218,39 @@ int carenv_policy_rollout(void *handle, const float *packed_weights, int n_envs,
     return launch(k_policy_rollout<1>);
 }
 
+/* Small batches: one warp per environment, network parameters in nn.Linear layout (k_policy_rollout_warp). */
+int carenv_policy_rollout_warp(void *handle, const float *w1a, const float *b1a, const float *w2a, const float *b2a,
+                               const float *w1c, const float *b1c, const float *w2c, const float *b2c, int n_envs,
+                               int n_steps, int env_offset, unsigned long long seed, unsigned long long step0,
+                               double *pos, double *vel, int32_t *ints, float *cur_obs, float *cur_term,
+                               float *cur_trunc, double reward_scale, float *obs_buf, float *act_buf, float *rew_buf,
+                               float *val_buf, float *term_buf, float *trunc_buf, float *logp_buf, float *last_val,
+                               float *u_dbg, void *stream) {
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(CARENV_E_INVAL, "null handle");
+    if (n_envs < 0 || n_steps < 0) return fail(CARENV_E_INVAL, "negative n_envs / n_steps");
+    if (n_envs == 0) return 0;
+    if (!w1a || !b1a || !w2a || !b2a || !w1c || !b1c || !w2c || !b2c || !pos || !vel || !ints || !cur_obs || !cur_term ||
+        !cur_trunc || !obs_buf || !act_buf || !rew_buf || !val_buf || !term_buf || !trunc_buf || !logp_buf)
+        return fail(CARENV_E_INVAL, "null pointer");
+    if (h->host.P.n_seg > 32)
+        return fail(CARENV_E_TRACK, "the warp-per-environment rollout kernel supports tracks with at most 32 wall segments");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(CARENV_E_NOGPU, "cannot select the handle's CUDA device");
+    const int table_bytes = (int)((h->smem_bytes + 15) / 16 * 16);
+    const size_t smem = (size_t)table_bytes + sizeof(float) * kWpFloats;
+    if (smem > 227 * 1024) return fail(CARENV_E_TRACK, "track tables too large for the warp-per-environment rollout kernel");
+    CU(cudaFuncSetAttribute(k_policy_rollout_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const ppo::Params W{w1a, b1a, w2a, b2a, w1c, b1c, w2c, b2c};
+    k_policy_rollout_warp<<<(n_envs + 3) / 4, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        h->host.P, h->dev, W, n_envs, n_steps, env_offset, seed, step0, reinterpret_cast<double2 *>(pos),
+        reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints), cur_obs, cur_term, cur_trunc, reward_scale, obs_buf,
+        act_buf, rew_buf, val_buf, term_buf, trunc_buf, logp_buf, last_val, u_dbg, h->d_stats, table_bytes,
+        h->pose_rows ? kObsPose : kObsFull);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 /* Test hook: D[128,256] = A[128,24] * B[256,24]^T on the tensor cores (tcgen05, kind::tf32). */
 int carenv_tc_gemm_test(const float *A, const float *B, float *D, void *stream) {
     if (!A || !B || !D) return fail(CARENV_E_INVAL, "null pointer");

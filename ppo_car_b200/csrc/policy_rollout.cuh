@@ -1101,3 +1101,157 @@ k_policy_rollout_tc3(const __grid_constant__ TrackParams P, const Tables G, cons
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<512>(tbase);
 }
+
+// ---- fused rollout for small batches: one WARP per environment --------------------------------------------------
+// The reference's own training shape is 24 environments (README: "about 35 minutes" for 200 epochs).  There a
+// thread-per-environment kernel is one long dependent chain on a nearly empty GPU (12 us per step in
+// k_policy_rollout_tc3).  Here a warp owns one environment, as in k_rollout_warp: lane j carries wall segment j
+// through the env step (per-ray extrema by integer REDUX) and, for the policy, hidden units j, j + 32, ... of both
+// nets (16 units per lane: first layer from shared-memory rows [unit][20] — conflict-free for consecutive lanes —,
+// ReLU, its share of the 256 -> 9 / 256 -> 1 sums), the ten partial sums are folded over the warp by an xor
+// butterfly (every lane ends with the same bits), every lane samples the same action.  Float32 CUDA cores only:
+// at 24 environments the tensor core has nothing to amortise its latency over.  The network parameters are read in
+// nn.Linear layout (no packing launch).
+constexpr int kWpRow = 20;                                   // first-layer row: 18 weights, bias, pad
+constexpr int kWpW2 = 12;                                    // actor second-layer row: W2[0..8][j], pad
+constexpr int kWpFloats = 2 * kHidden * kWpRow + kHidden * kWpW2 + kHidden + 12;   // 13,580 floats = 54,320 B
+
+__global__ void __launch_bounds__(128)
+k_policy_rollout_warp(const __grid_constant__ TrackParams P, const Tables G, const ppo::Params W, int n_envs, int n_steps,
+                      int env_offset, unsigned long long seed, unsigned long long step0, double2 *__restrict__ pos,
+                      double2 *__restrict__ vel, int4 *__restrict__ ints, float *__restrict__ cur_obs,
+                      float *__restrict__ cur_term, float *__restrict__ cur_trunc, double reward_scale,
+                      float *__restrict__ obs_buf, float *__restrict__ act_buf, float *__restrict__ rew_buf,
+                      float *__restrict__ val_buf, float *__restrict__ term_buf, float *__restrict__ trunc_buf,
+                      float *__restrict__ logp_buf, float *__restrict__ last_val, float *__restrict__ u_dbg,
+                      unsigned long long *stats, int table_bytes, int obs_mode) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *sw1 = reinterpret_cast<float *>(smem + table_bytes);   // [512][20]: rows 0..255 actor, 256..511 critic
+    float *sw2 = sw1 + 2 * kHidden * kWpRow;                      // [256][12]
+    float *swc = sw2 + kHidden * kWpW2;                           // [256]
+    float *stail = swc + kHidden;                                 // b2a[0..8], 0, b2c, 0
+    for (int i = threadIdx.x; i < 2 * kHidden * kWpRow; i += blockDim.x) {
+        const int r = i / kWpRow, c = i - r * kWpRow, j = r & (kHidden - 1);
+        const float *w1 = r < kHidden ? W.w1a : W.w1c, *b1 = r < kHidden ? W.b1a : W.b1c;
+        sw1[i] = c < kObsDim ? w1[j * kObsDim + c] : (c == kObsDim ? b1[j] : 0.0f);
+    }
+    for (int i = threadIdx.x; i < kHidden * kWpW2; i += blockDim.x) {
+        const int j = i / kWpW2, q = i - j * kWpW2;
+        sw2[i] = q < kActions ? W.w2a[q * kHidden + j] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < kHidden; i += blockDim.x) swc[i] = W.w2c[i];
+    if (threadIdx.x < 12) stail[threadIdx.x] = threadIdx.x < kActions ? W.b2a[threadIdx.x] : (threadIdx.x == 10 ? W.b2c[0] : 0.0f);
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);      // ends with __syncthreads()
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= n_envs) return;
+
+    WarpSeg ws;
+    ws.active = lane < P.n_seg;
+    ws.f = G.segf[ws.active ? lane : 0];
+    ws.g = G.segd[ws.active ? lane : 0];
+    EnvState s;
+    {
+        const double2 p = pos[e], v = vel[e];
+        const int4 q = ints[e];
+        s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y;
+        s.k = q.x; s.t = q.y; s.next_gate = q.z; s.passed = q.w;
+    }
+    float obs[kObsDim];
+    {
+        const float2 *src = reinterpret_cast<const float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+        for (int i = 0; i < kObsDim / 2; ++i) { const float2 v = src[i]; obs[2 * i] = v.x; obs[2 * i + 1] = v.y; }
+    }
+    float tc_ = cur_term[e], uc = cur_trunc[e];
+    const uint32_t gid = (uint32_t)(env_offset + e);
+    unsigned long long *my_stats = lane == 0 ? stats : nullptr;
+
+    // pre-activation of one hidden unit (row of sw1) for the observation in `obs`
+    auto unit = [&](const float *row) {
+        const float4 *r4 = reinterpret_cast<const float4 *>(row);
+        const float4 w0 = r4[0], w1 = r4[1], w2 = r4[2], w3 = r4[3], w4 = r4[4];
+        float pa = w4.z, pb = 0.0f, pc = 0.0f;                                   // bias; three chains
+        pa = fmaf(w0.x, obs[0], pa); pb = fmaf(w0.y, obs[1], pb); pc = fmaf(w0.z, obs[2], pc);
+        pa = fmaf(w0.w, obs[3], pa); pb = fmaf(w1.x, obs[4], pb); pc = fmaf(w1.y, obs[5], pc);
+        pa = fmaf(w1.z, obs[6], pa); pb = fmaf(w1.w, obs[7], pb); pc = fmaf(w2.x, obs[8], pc);
+        pa = fmaf(w2.y, obs[9], pa); pb = fmaf(w2.z, obs[10], pb); pc = fmaf(w2.w, obs[11], pc);
+        pa = fmaf(w3.x, obs[12], pa); pb = fmaf(w3.y, obs[13], pb); pc = fmaf(w3.z, obs[14], pc);
+        pa = fmaf(w3.w, obs[15], pa); pb = fmaf(w4.x, obs[16], pb); pc = fmaf(w4.y, obs[17], pc);
+        return fmaxf((pa + pb) + pc, 0.0f);
+    };
+    // both nets for `obs`: logits (+ bias) and value in every lane
+    auto forward = [&](PolicyOut &po, bool actor) {
+        float part[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) part[q] = 0.0f;
+#pragma unroll 2
+        for (int i = 0; i < kHidden / 32; ++i) {
+            const int j = lane + 32 * i;
+            if (actor) {
+                const float h = unit(sw1 + j * kWpRow);
+                const float4 *v4 = reinterpret_cast<const float4 *>(sw2 + j * kWpW2);
+                const float4 v0 = v4[0], v1 = v4[1], v2 = v4[2];
+                part[0] = fmaf(v0.x, h, part[0]); part[1] = fmaf(v0.y, h, part[1]); part[2] = fmaf(v0.z, h, part[2]);
+                part[3] = fmaf(v0.w, h, part[3]); part[4] = fmaf(v1.x, h, part[4]); part[5] = fmaf(v1.y, h, part[5]);
+                part[6] = fmaf(v1.z, h, part[6]); part[7] = fmaf(v1.w, h, part[7]); part[8] = fmaf(v2.x, h, part[8]);
+            }
+            part[9] = fmaf(swc[j], unit(sw1 + (kHidden + j) * kWpRow), part[9]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 10; ++q) part[q] += __shfl_xor_sync(0xffffffffu, part[q], o);
+        }
+#pragma unroll
+        for (int q = 0; q < kActions; ++q) po.logit[q] = part[q] + stail[q];
+        po.logit[9] = 0.0f;
+        po.value = part[9] + stail[10];
+    };
+
+    PolicyOut po;
+    for (int t = 0; t < n_steps; ++t) {
+        const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+        forward(po, true);
+        const unsigned long long gs = step0 + (unsigned long long)t;
+        const uint32_t bits = philox_uniform_bits((uint32_t)seed, (uint32_t)(seed >> 32), gid, (uint32_t)gs,
+                                                  (uint32_t)(gs >> 32), 0x43415245u);
+        const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
+        float logp, us;
+        const int a = sample_action(po, u, logp, us);
+        if (lane == 0) {
+            if (obs_mode == kObsPose) {
+                store_pose(reinterpret_cast<PoseRec *>(obs_buf) + idx, s, obs[2], obs[3]);
+            } else {
+                float2 *dst = reinterpret_cast<float2 *>(obs_buf + idx * kObsDim);
+#pragma unroll
+                for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+            }
+            act_buf[idx] = (float)a;
+            val_buf[idx] = po.value;
+            logp_buf[idx] = logp;
+            term_buf[idx] = tc_;
+            trunc_buf[idx] = uc;
+            if (u_dbg) u_dbg[idx] = u;
+        }
+        StepResult o;
+        env_step<kWarpPerEnv>(s, a, reward_scale, P, T, o, my_stats, &ws);
+        if (lane == 0) rew_buf[idx] = o.reward;
+#pragma unroll
+        for (int i = 0; i < kObsDim; ++i) obs[i] = o.obs[i];
+        tc_ = o.terminated ? 1.0f : 0.0f;
+        uc = o.truncated ? 1.0f : 0.0f;
+    }
+    if (last_val) forward(po, false);                        // bootstrap value of the final observation (critic only)
+    if (lane == 0) {
+        pos[e] = make_double2(s.px, s.py);
+        vel[e] = make_double2(s.vx, s.vy);
+        ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+        float2 *dst = reinterpret_cast<float2 *>(cur_obs + (size_t)e * kObsDim);
+#pragma unroll
+        for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(obs[2 * i], obs[2 * i + 1]);
+        cur_term[e] = tc_;
+        cur_trunc[e] = uc;
+        if (last_val) last_val[e] = po.value;
+    }
+}

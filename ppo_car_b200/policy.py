@@ -141,3 +141,40 @@ def fused_rollout(env, packed: torch.Tensor, buf, cur_obs: torch.Tensor, cur_ter
                 _p(buf.trunc_buf), _p(buf.logprob_buf), _p(last_val), _p(u_dbg), env._stream())
     _lib.check(rc, "carenv_policy_rollout_tc" if tensor_cores else "carenv_policy_rollout")
     buf.ptr = T
+
+
+WARP_ROLLOUT_MAX_ENVS = 4096        # crossover against the tensor-core kernel (benchmarks/fused_small.py)
+
+
+def fused_rollout_warp(env, actor, critic, buf, cur_obs: torch.Tensor, cur_term: torch.Tensor, cur_trunc: torch.Tensor,
+                       seed: int, step0: int, env_offset: int = 0, last_val: torch.Tensor | None = None,
+                       u_dbg: torch.Tensor | None = None) -> None:
+    """:func:`fused_rollout` for small batches (C ABI carenv_policy_rollout_warp): one warp per environment, the
+    network's parameters read in place (no packing).  Tracks with at most 32 wall segments."""
+    n, T = env.num_envs, buf.capacity
+    params = [actor[0].weight, actor[0].bias, actor[2].weight, actor[2].bias,
+              critic[0].weight, critic[0].bias, critic[2].weight, critic[2].bias]
+    if [tuple(p.shape) for p in params] != [(HIDDEN, OBS), (HIDDEN,), (ACTIONS, HIDDEN), (ACTIONS,), (HIDDEN, OBS),
+                                            (HIDDEN,), (1, HIDDEN), (1,)]:
+        raise ValueError("fused rollout supports the reference network only: 18-256-9 actor, 18-256-1 critic")
+    if any(p.dtype != torch.float32 or not p.is_contiguous() or p.device != env.device for p in params):
+        raise ValueError(f"parameters must be contiguous float32 tensors on {env.device}")
+    for name, t, shape in (("cur_obs", cur_obs, (n, OBS)), ("cur_term", cur_term, (n,)), ("cur_trunc", cur_trunc, (n,)),
+                           ("last_val", last_val, (n,)), ("u_dbg", u_dbg, (T, n))):
+        if t is not None and (tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_contiguous()
+                              or t.device != env.device):
+            raise ValueError(f"{name} must be a contiguous float32 tensor of shape {shape} on {env.device}")
+    compact = bool(getattr(buf, "compact_obs", False))
+    rows = buf.pose_buf if compact else buf.obs_buf
+    if tuple(rows.shape) != ((T, n, 4) if compact else (T, n, OBS)):
+        raise ValueError("buffer shape does not match the environment")
+    env.set_option("pose_rows", int(compact))
+    L = _lib.lib()
+    with torch.cuda.device(env.device):
+        rc = L.carenv_policy_rollout_warp(env._handle, *[_p(p) for p in params], n, T, int(env_offset),
+                                          int(seed) & (2 ** 64 - 1), int(step0), _p(env.pos), _p(env.vel), _p(env.ints),
+                                          _p(cur_obs), _p(cur_term), _p(cur_trunc), float(env.reward_scaling), _p(rows),
+                                          _p(buf.act_buf), _p(buf.rew_buf), _p(buf.val_buf), _p(buf.term_buf),
+                                          _p(buf.trunc_buf), _p(buf.logprob_buf), _p(last_val), _p(u_dbg), env._stream())
+    _lib.check(rc, "carenv_policy_rollout_warp")
+    buf.ptr = T

@@ -186,8 +186,13 @@ def train(args) -> list[dict]:
             next_trunc.copy_(tr)
 
     packed = last_val = None
+    warp_rollout = False
     if args.fused_rollout:
-        from .policy import fused_rollout, pack_policy_weights, pack_policy_weights_tc
+        from .policy import (WARP_ROLLOUT_MAX_ENVS, fused_rollout, fused_rollout_warp, pack_policy_weights,
+                             pack_policy_weights_tc)
+
+        # small shards (the reference's 24 environments): one warp per environment, parameters read in place
+        warp_rollout = (not args.fused_cuda_cores and n <= WARP_ROLLOUT_MAX_ENVS and len(envs.track.walls) <= 32)
 
         # tensor-core kernel (256- or 512-environment CTAs, chosen by the library from the shard size); it is also
         # the faster one for tiny shards (24 envs: 12.7 vs 14.4 us per step, benchmarks/fused_rollout.py)
@@ -215,7 +220,11 @@ def train(args) -> list[dict]:
         for epoch in range(1, args.n_epochs + 1):
             # ---- rollout
             with torch.no_grad():
-                if packed is not None:
+                if warp_rollout:
+                    fused_rollout_warp(envs, agent.actor, agent.critic, buf, next_obs, next_term, next_trunc,
+                                       seed=args.seed, step0=(epoch - 1) * T, env_offset=lo, last_val=last_val)
+                    boot = last_val.reshape(1, -1)
+                elif packed is not None:
                     pack_policy(agent.actor, agent.critic, out=packed)
                     fused_rollout(envs, packed, buf, next_obs, next_term, next_trunc, seed=args.seed,
                                   step0=(epoch - 1) * T, env_offset=lo, last_val=last_val)

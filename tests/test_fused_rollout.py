@@ -94,6 +94,67 @@ def test_fused_rollout_matches_torch_policy_and_env_kernel(tracks_dir, n, tensor
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,track_name", [(24, "big_track.json"), (257, "big_track.json"), (50, "track.json")])
+def test_warp_per_environment_fused_rollout(tracks_dir, n, track_name):
+    """k_policy_rollout_warp (small batches: lane = wall segment in the env step, lane = 16 hidden units in the
+    policy) against torch float32, the inverse CDF of the recorded uniform, a replay through the plain rollout kernel
+    and a sharded run."""
+    dev = torch.device("cuda")
+    path = os.path.join(tracks_dir, track_name)
+    T = 300
+    torch.manual_seed(3)
+    net = ActorCritic(18, 9).to(dev)
+    with torch.no_grad():
+        net.actor[2].weight.mul_(40.0)
+        net.actor[2].bias.copy_(torch.linspace(-1, 1, 9))
+        net.critic[2].bias.fill_(0.3)
+    env = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1, float_flags=True)
+    buf = ppo_car_b200.Buffer((18,), T, n, dev)
+    cur_obs = env.reset()[0].clone()
+    cur_term, cur_trunc = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    last_val, u = torch.empty(n, device=dev), torch.empty((T, n), device=dev)
+    ppo_car_b200.fused_rollout_warp(env, net.actor, net.critic, buf, cur_obs, cur_term, cur_trunc, seed=11, step0=5,
+                                    last_val=last_val, u_dbg=u)
+    torch.cuda.synchronize()
+    assert buf.ptr == T
+    with torch.no_grad():
+        logits = net.actor(buf.obs_buf.view(-1, 18)).view(T, n, 9)
+        val = net.critic(buf.obs_buf.view(-1, 18)).view(T, n)
+        logp_all = torch.log_softmax(logits, -1)
+        assert torch.allclose(last_val, net.critic(cur_obs).view(-1), rtol=1e-5, atol=1e-5)
+    act = buf.act_buf.long()
+    assert torch.allclose(buf.val_buf, val, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(buf.logprob_buf, logp_all.gather(-1, act.unsqueeze(-1)).squeeze(-1), rtol=1e-5, atol=1e-5)
+    cdf = torch.softmax(logits, -1).cumsum(-1)
+    expect = (u.unsqueeze(-1) >= cdf).sum(-1).clamp(max=8)
+    near = ((cdf - u.unsqueeze(-1)).abs() < 1e-5).any(-1)
+    assert ((expect == act) | near).all() and near.float().mean() < 1e-3
+    assert len(torch.unique(act)) == 9
+    env2 = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1, float_flags=True)
+    obs0 = env2.reset()[0].clone()
+    out = env2.rollout(act.to(torch.uint8))
+    assert torch.equal(buf.obs_buf[0], obs0) and torch.equal(buf.obs_buf[1:], out["obs"][:-1])
+    assert torch.equal(buf.rew_buf, out["reward"])
+    assert torch.equal(buf.term_buf[1:], out["terminated"][:-1]) and torch.equal(buf.trunc_buf[1:], out["truncated"][:-1])
+    assert torch.equal(cur_obs, out["obs"][-1]) and torch.equal(env.pos, env2.pos) and torch.equal(env.ints, env2.ints)
+    half = n // 2
+    env3 = ppo_car_b200.VecCarEnv(n - half, path, reward_scaling=0.1, float_flags=True)
+    buf3 = ppo_car_b200.Buffer((18,), T, n - half, dev)
+    o3 = env3.reset()[0].clone()
+    z = torch.zeros(n - half, device=dev)
+    ppo_car_b200.fused_rollout_warp(env3, net.actor, net.critic, buf3, o3, z.clone(), z.clone(), seed=11, step0=5,
+                                    env_offset=half)
+    assert torch.equal(buf3.act_buf, buf.act_buf[:, half:]) and torch.equal(buf3.logprob_buf, buf.logprob_buf[:, half:])
+    # the same random stream as the tensor-core kernels: identical uniforms
+    env4 = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1, float_flags=True)
+    buf4 = ppo_car_b200.Buffer((18,), T, n, dev)
+    o4, u4 = env4.reset()[0].clone(), torch.empty((T, n), device=dev)
+    ppo_car_b200.fused_rollout(env4, ppo_car_b200.pack_policy_weights_tc(net.actor, net.critic), buf4, o4,
+                               torch.zeros(n, device=dev), torch.zeros(n, device=dev), seed=11, step0=5, u_dbg=u4)
+    assert torch.equal(u, u4)
+
+
+@pytest.mark.gpu
 def test_two_thread_kernels_agree_bit_for_bit(tracks_dir):
     """k_policy_rollout_tc2 and k_policy_rollout_tc3 sum the logits in the same order ((units 0..127) + (units
     128..255) + bias) and the values in the order of every other kernel: identical rollouts, bit for bit; the

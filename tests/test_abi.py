@@ -73,6 +73,21 @@ def test_bad_arguments_return_error_codes():
     assert L.carenv_step_host_records(None, 1, None, None, None, None, 0, 1.0, None, None, None, None) == -1
     assert L.carenv_step_records(None, 1, None, None, None, None, 0, 1.0, None, None, None, None) == -1
     assert L.carenv_host_alloc(16, None) == -1 and L.carenv_host_free(None) == 0
+    # the policy / PPO entry points
+    comm, hbuf = C.c_void_p(), C.create_string_buffer(64)
+    assert L.carenv_ppo_comm_create(0, 0, C.byref(comm), hbuf) == -1 and not comm.value      # world out of range
+    assert L.carenv_ppo_comm_create(9, 0, C.byref(comm), hbuf) == -1
+    assert L.carenv_ppo_comm_create(2, 2, C.byref(comm), hbuf) == -1                         # rank out of range
+    assert L.carenv_ppo_comm_create(2, 0, None, hbuf) == -1
+    assert L.carenv_ppo_comm_connect(None, hbuf) == -1 and L.carenv_ppo_comm_destroy(None) == 0
+    assert L.carenv_ppo_epoch_workspace_floats() > 160 * 12298
+    epoch_args = [None] * 14 + [512, 80, 0.2, 0.5, 0.001, None, None, None, None, 0.9, 0.999, 1e-5, 1.0, None, None, None,
+                                None, 0, None, None]
+    assert L.carenv_ppo_epoch(*epoch_args) == -1 and b"null" in L.carenv_last_error()
+    epoch_args[14] = 5000                                                                    # batch out of range
+    assert L.carenv_ppo_epoch(*epoch_args) == -1 and b"batch" in L.carenv_last_error()
+    assert L.carenv_policy_rollout_warp(*([None] * 9), 4, 4, 0, 0, 0, *([None] * 6), 1.0, *([None] * 10)) == -1
+    assert L.carenv_policy_rollout_tc(None, None, 4, 4, 0, 0, 0, *([None] * 6), 1.0, *([None] * 10)) == -1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

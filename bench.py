@@ -32,7 +32,8 @@ such as 8 x 32 measure 2-18 % less, depending on the shard size).
             is reported beside it (`port_value`).  Without oracle/_ref: the port, kind "port".
   configs   BASELINE.json's other configurations, measured after the timed region on rank 0:
             config 2 (24 envs x 1024 steps), config 3 (65,536 envs x 1024 steps rollout + GAE) and, at
-            --gpus 8, config 5 (PPO loop, 262,144 envs, fused rollout + fused update + NCCL all-reduce)
+            --gpus 8, config 5 (PPO loop, 262,144 envs: fused rollout, GAE kernel, all minibatch updates of an
+            epoch in one launch with the gradient all-reduce over NVLink peer memory inside the kernel)
 """
 from __future__ import annotations
 

@@ -533,7 +533,9 @@ def run_ours(args):
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_nominal, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_nominal, "traffic": traffic,
                          "traffic_note": traffic_note + f"; algorithmic bytes per launch = {bytes_per_launch}",
-                         "kernel": "k_rollout_tab<uint8,uint8,6>", "launch_ms": launch_ms,
+                         "kernel": ("k_rollout_tab_sliced<uint8,uint8,6>"      # the library's choice (launch_rollout_tab)
+                                    if ((n + 31) // 32) // 148 >= 16 and chunk >= 4
+                                    else "k_rollout_tab<uint8,uint8,6>"), "launch_ms": launch_ms,
                          "launch_ms_min": min(per_launch_ms) / launches, "launch_ms_max": max(per_launch_ms) / launches,
                          "flop_per_env_step": FLOP_PER_ENV_STEP,
                          "peak_source": f"nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no "

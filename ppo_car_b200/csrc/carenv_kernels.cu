@@ -82,6 +82,9 @@ struct Handle {
     int pose_rows;            // fused rollout kernels: obs_buf holds 32-byte pose records instead of observations
     int warp_per_env;         // 0 = warp-per-environment kernel for small batches, 1 = always, -1 = never
     struct HostStep *hs;      // staging buffers / streams of carenv_step_host (allocated on first use)
+    int *d_flags;             // k_rollout_tab_sliced: "head part done" flag per 32-environment job (allocated on first use)
+    size_t flags_cap;         // ints in d_flags
+    int tab_slice;            // 0 = time-sliced table kernel where it applies, 1 = wherever possible, -1 = never
 };
 
 // Resources of the host-buffer step path (carenv_step_host): device staging for one step of `cap` environments,
@@ -364,6 +367,113 @@ k_rollout_tab(const __grid_constant__ TrackParams P, const Tables G, const float
         pos[e] = make_double2(s.px, s.py);
         vel[e] = make_double2(s.vx, s.vy);
         ints[e] = make_int4(s.k, s.t, s.next_gate, s.passed);
+    }
+}
+
+// k_rollout_tab with the work of an SM spread EVENLY over its 16 warps in units of env-STEPS instead of whole blocks
+// of environments.  With blocks, an SM that owns W warps' worth of environments runs ceil(W / 16) rounds and the last
+// round is short-handed: 131,072 envs on 148 SMs (the 8-GPU shard of the 1 M-env job) = 27.7 warps per SM = a round
+// with four warps per scheduler and one with three, which run at 0.98 and 0.84 warp-steps/us — 6 % lost.  Here a
+// "job" is 32 consecutive environments x n_steps steps; the W jobs of an SM are laid end to end (W x n_steps
+// warp-steps) and cut into 16 equal intervals, one per warp (McNaughton's wrap-around rule for preemptible jobs on
+// identical machines).  A job that straddles the boundary between warp w and warp w + 1 is split IN TIME: warp w + 1
+// runs its first steps at the start of its interval, stores the state (the pos / vel / ints arrays themselves are the
+// hand-over buffer) and raises the job's flag; warp w runs the remaining steps at the END of its interval (an interval
+// is at least n_steps long, so the first part has finished by then; the flag makes it safe).  Every warp is busy for
+// the same number of steps and every scheduler keeps four warps until the very end.  Per-environment arithmetic is
+// untouched: results are bit-identical to k_rollout_tab / k_rollout.
+template <typename ActT, typename FlagT, int U>
+__global__ void __launch_bounds__(kTabThreads, 1)
+k_rollout_tab_sliced(const __grid_constant__ TrackParams P, const Tables G, const float4 *__restrict__ den4, int n_pairs,
+                     int row_f4, int copies, int table_bytes, int n_envs, int n_steps, int *__restrict__ flags,
+                     double2 *__restrict__ pos, double2 *__restrict__ vel, int4 *__restrict__ ints,
+                     const ActT *__restrict__ actions, double reward_scale, float *__restrict__ obs_out,
+                     float *__restrict__ rew_out, FlagT *__restrict__ term_out, FlagT *__restrict__ trunc_out,
+                     int4 *__restrict__ info_out, int4 *__restrict__ rec_out, unsigned long long *stats, int obs_mode) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem);
+    const int t_off = (int)(((s0 + (uint32_t)table_bytes + 127u) & ~127u) - s0);
+    float4 *tab = reinterpret_cast<float4 *>(smem + t_off);
+    const int copy_f4 = kHeadings * row_f4 + 1;
+    for (int i = threadIdx.x; i < kHeadings * n_pairs; i += blockDim.x) {
+        const float4 v = den4[i];
+        const int k = i / n_pairs, jp = i - k * n_pairs;
+        for (int c = 0; c < copies; ++c) tab[c * copy_f4 + k * row_f4 + jp] = v;
+    }
+    const Tables T = stage_tables(G, P.n_gates, P.n_seg, smem);      // ends with __syncthreads()
+    const TabView tv{tab + (threadIdx.x & (copies - 1)) * copy_f4, row_f4};
+
+    // (the warp index through a shuffle: the compiler then knows that it — and with it every item bound below, the
+    // trip count of the step loop included — is warp-uniform; derived from threadIdx alone the loop counted as
+    // divergent and the wall tests lost their uniform-register operands: 8 % slower)
+    const int slot = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31, n_slots = blockDim.x >> 5;
+    const int jobs_total = (n_envs + 31) >> 5;
+    const int job_lo = (int)((long long)blockIdx.x * jobs_total / gridDim.x);
+    const int job_hi = (int)((long long)(blockIdx.x + 1) * jobs_total / gridDim.x);
+    // This warp's interval [lo, hi) of the SM's job_count x n_steps warp-steps, as a list of items:
+    //   the job cut by lo (the previous warp holds its LAST steps): its first steps   [item first_job, steps 0 .. head_len)
+    //   whole jobs                                                                    [first_job + has_head .. last_full]
+    //   the job cut by hi (the next warp runs its first steps): its last steps        [item tail_job, steps n - tail_len .. n)
+    int first_job, head_len, last_full, tail_len;
+    {
+        const long long total = (long long)(job_hi - job_lo) * n_steps;
+        const long long quota = (total + n_slots - 1) / n_slots;                 // >= n_steps (the launcher checks)
+        const long long lo = min(total, (long long)slot * quota), hi = min(total, lo + quota);
+        first_job = (int)(lo / n_steps);
+        const int off = (int)(lo - (long long)first_job * n_steps);
+        head_len = off > 0 ? n_steps - off : 0;
+        last_full = (int)(hi / n_steps) - 1;                                      // last job that ends at or before hi
+        tail_len = (int)(hi - (long long)(last_full + 1) * n_steps);
+        if (lo >= hi) { head_len = 0; tail_len = 0; last_full = first_job - 1; }
+    }
+    // (item bookkeeping in shared memory instead of registers was measured: fewer spills, 1.5 % slower)
+    const int n_items = (last_full + 1 - first_job) + (tail_len > 0 ? 1 : 0);     // the head item is job first_job itself
+    for (int it = 0; it < n_items; ++it) {
+        const int job = first_job + it;
+        const bool head = it == 0 && head_len > 0, tail = job > last_full;
+        const int t0 = tail ? n_steps - tail_len : 0, t1 = head ? head_len : n_steps;
+        const int e = ((job_lo + job) << 5) + lane;
+        // (only the grid's very last job can have lanes past the end, and it is the last item of every warp that touches
+        // it — `break` keeps the loop body provably convergent, which the uniform-register operands of the wall tests need)
+        if (e >= n_envs) break;
+        int *flag = flags + job_lo + job;
+        if (tail) {                                          // the first part's state must be in memory
+            int spins = 0;
+            while (*reinterpret_cast<volatile int *>(flag) == 0)
+                if (++spins > (1 << 28)) __trap();           // a scheduling error must not hang the GPU box
+            __threadfence();
+        }
+        EnvState s;
+        {
+            const double2 pp = __ldcg(pos + e), v = __ldcg(vel + e);
+            const int4 qq = __ldcg(ints + e);
+            s.px = pp.x; s.py = pp.y; s.vx = v.x; s.vy = v.y;
+            s.k = qq.x; s.t = qq.y; s.next_gate = qq.z; s.passed = qq.w;
+        }
+        int a_next = (int)actions[(size_t)t0 * (size_t)n_envs + (size_t)e];
+        for (int t = t0; t < t1; ++t) {
+            const size_t idx = (size_t)t * (size_t)n_envs + (size_t)e;
+            const int a = a_next;
+            if (t + 1 < t1) a_next = (int)actions[idx + (size_t)n_envs];
+            StepResult o;
+            env_step<U, true>(s, a, reward_scale, P, T, o, stats, nullptr, &tv);
+            if (obs_mode == kObsFull) {
+                float2 *dst = reinterpret_cast<float2 *>(obs_out + idx * kObsDim);
+#pragma unroll
+                for (int i = 0; i < kObsDim / 2; ++i) dst[i] = make_float2(o.obs[2 * i], o.obs[2 * i + 1]);
+            } else if (obs_mode == kObsPose) {
+                store_pose(reinterpret_cast<PoseRec *>(obs_out) + idx, s, o.obs[2], o.obs[3]);
+            }
+            store_step(o, idx, rew_out, term_out, trunc_out, info_out, rec_out);
+        }
+        __stcg(pos + e, make_double2(s.px, s.py));
+        __stcg(vel + e, make_double2(s.vx, s.vy));
+        __stcg(ints + e, make_int4(s.k, s.t, s.next_gate, s.passed));
+        if (head) {                                          // publish: every lane's state first, then the flag
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile int *>(flag) = 1;
+        }
     }
 }
 
@@ -682,6 +792,49 @@ int launch_rollout_tab(Handle *h, int U, int n_envs, int n_steps, double *pos, d
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int block = h->block > 0 ? h->block * 4 : kTabThreads;           // tuning hook (block is 0..128: x4)
+    // Time-sliced distribution (k_rollout_tab_sliced) when every SM gets at least one 32-environment job per warp, so
+    // that no job is cut twice; not for the final-observation variant (cur_fobs never reaches this function).
+    {
+        const long long jobs = (n_envs + 31) / 32;
+        // (single steps — the host-buffer step's sub-ranges — stay with the block scheme: nothing to balance over time
+        // and its prologue is shorter; measured 7 % on the end-to-end rate)
+        const bool fits = jobs / sms >= block / 32 && block == kTabThreads && n_steps >= 4;
+        if (h->tab_slice >= 0 && fits) {
+            const size_t need = (size_t)jobs;
+            bool ok = true;
+            {
+                if (h->flags_cap < need) {
+                    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+                    cudaStreamIsCapturing(stream, &cap);
+                    if (cap != cudaStreamCaptureStatusNone) {
+                        ok = false;                          // no allocation inside a graph capture: block scheme
+                    } else {
+                        if (h->d_flags) cudaFree(h->d_flags);
+                        h->d_flags = nullptr; h->flags_cap = 0;
+                        CU(cudaMalloc(reinterpret_cast<void **>(&h->d_flags), need * sizeof(int)));
+                        h->flags_cap = need;
+                    }
+                }
+                if (ok) CU(cudaMemsetAsync(h->d_flags, 0, need * sizeof(int), stream));
+            }
+            if (ok) {
+                const size_t smem_s = total(copies);
+                auto launch_s = [&](auto kern) -> int {
+                    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+                    kern<<<sms, block, smem_s, stream>>>(
+                        h->host.P, h->dev, h->d_den4, n_pairs, row_f4, copies, table_bytes, n_envs, n_steps, h->d_flags,
+                        reinterpret_cast<double2 *>(pos), reinterpret_cast<double2 *>(vel), reinterpret_cast<int4 *>(ints),
+                        static_cast<const ActT *>(actions), reward_scale, obs_out, reward_out, static_cast<FlagT *>(term_out),
+                        static_cast<FlagT *>(trunc_out), reinterpret_cast<int4 *>(info_out), h->cur_rec, h->d_stats, obs_mode);
+                    CU(cudaGetLastError());
+                    return 0;
+                };
+                if (U == 6) return launch_s(k_rollout_tab_sliced<ActT, FlagT, 6>);
+                if (U == 4) return launch_s(k_rollout_tab_sliced<ActT, FlagT, 4>);
+                return launch_s(k_rollout_tab_sliced<ActT, FlagT, 2>);
+            }
+        }
+    }
     // A round = one block per SM.  Its duration is set by the warps per SCHEDULER (a block of 448 environments takes as
     // long as one of 512), so all rounds but the last are full blocks and the last round's blocks are the smallest
     // multiple of 128 environments that covers the remainder: 131,072 envs on 148 SMs = 148 x 512 + 148 x 384.
@@ -800,7 +953,7 @@ int carenv_create(const double *walls, int n_walls, const double *gates, int n_g
     if (device < 0 || device >= n_dev) return fail(CARENV_E_INVAL, "device index out of range");
     Handle *h = new Handle();
     h->device = device;
-    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->tc_stagger = -1; h->pose_rows = 0; h->warp_per_env = 0; h->hs = nullptr; h->d_den4 = nullptr; h->tab = 0; h->cur_rec = nullptr; h->cur_fobs = nullptr; h->host_ranges = 0;
+    h->d_blob = nullptr; h->d_stats = nullptr; h->force_generic = 0; h->max_unroll = 0; h->block = 0; h->smem_pad = 0; h->tc_tiles = 0; h->tc_stagger = -1; h->pose_rows = 0; h->warp_per_env = 0; h->hs = nullptr; h->d_den4 = nullptr; h->tab = 0; h->cur_rec = nullptr; h->cur_fobs = nullptr; h->host_ranges = 0; h->d_flags = nullptr; h->flags_cap = 0; h->tab_slice = 0;
     if (build_host_track(walls, n_walls, gates, n_gates, init_x, init_y, init_angle_deg, h->host) != 0) {
         delete h;
         return fail(CARENV_E_TRACK, "malformed track");
@@ -855,6 +1008,7 @@ int carenv_destroy(void *handle) {
         DeviceGuard guard(h->device);
         cudaFree(h->d_blob);
         cudaFree(h->d_stats);
+        if (h->d_flags) cudaFree(h->d_flags);
         if (h->hs) { h->hs->release(); delete h->hs; }
     }
     delete h;
@@ -1222,6 +1376,7 @@ int carenv_set_option(void *handle, const char *name, int value) {
     if (std::string(name) == "tab") { h->tab = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
     if (std::string(name) == "warp_per_env") { h->warp_per_env = value > 0 ? 1 : (value < 0 ? -1 : 0); return 0; }
     if (std::string(name) == "tc_stagger") { h->tc_stagger = value; return 0; }
+    if (std::string(name) == "tab_slice") { h->tab_slice = value; return 0; }
     if (std::string(name) == "tc_tiles") {
         if (value != 0 && (value < 2 || value > 5)) return fail(CARENV_E_INVAL, "tc_tiles must be 0 or 2..5");
         h->tc_tiles = value; return 0;

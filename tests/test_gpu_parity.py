@@ -792,3 +792,30 @@ def test_numpy_step_records_debug_info_copy_outputs_and_device_records(tracks_di
     rec = rec_dev.cpu().numpy().view(ppo_car_b200.VecCarEnv._REC_DTYPE).reshape(n)
     assert np.array_equal(rec["reward"], rh) and rec["reward"].dtype == np.float64 and np.array_equal(rec["terminated"], teh)
     assert np.array_equal(rec["time_passed"], ih["time_passed"]) and np.array_equal(obs_dev.cpu().numpy(), oh)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,T", [(75_776, 37), (100_003, 64), (200_003, 5), (131_072, 256)])
+def test_time_sliced_table_kernel_is_bit_identical(tracks_dir, n, T):
+    """k_rollout_tab_sliced (an SM's env-steps cut into 16 equal per-warp intervals, jobs that straddle two warps
+    split in time with a state hand-over through memory) against the block-round table kernel: identical outputs and
+    final state, at sizes with ragged last jobs and step counts that put the cuts in the middle of jobs; a second
+    launch continues from the handed-over state."""
+    path = os.path.join(tracks_dir, "big_track.json")
+    g = torch.Generator(device="cuda").manual_seed(n + T)
+    acts = torch.randint(0, 9, (2, T, n), generator=g, device="cuda", dtype=torch.uint8)
+    outs = []
+    for opt in (-1, 0):
+        env = ppo_car_b200.VecCarEnv(n, path, reward_scaling=0.1)
+        env.set_option("tab_slice", opt)
+        env.reset()
+        res = [env.rollout(acts[i], store_info=True) for i in range(2)]
+        outs.append(([{k: (v.clone() if torch.is_tensor(v) else {kk: vv.clone() for kk, vv in v.items()})
+                       for k, v in r.items()} for r in res], env.pos.clone(), env.vel.clone(), env.ints.clone()))
+    (ra, pa, va, ia), (rb, pb, vb, ib) = outs
+    assert torch.equal(pa, pb) and torch.equal(va, vb) and torch.equal(ia, ib)
+    for a, b in zip(ra, rb):
+        for k in ("obs", "reward", "terminated", "truncated"):
+            assert torch.equal(a[k], b[k]), k
+        for k in a["info"]:
+            assert torch.equal(a["info"][k], b["info"][k]), k

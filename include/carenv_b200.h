@@ -181,6 +181,7 @@ int carenv_render(void *handle, int n_outer_segments, int n_frames, const int32_
  * many 128-environment groups per CTA, 3 = k_policy_rollout_tc2: environment + policy thread per environment, 5 =
  * k_policy_rollout_tc3: second-layer weight loads shared by the two environments of a tensor-memory lane — variants 3
  * and 5 give the same bits, 2 and 4 differ from them in the last bits of the logits only);
+ * "tab_slice" = -1 keeps the block-round table kernel where the time-sliced one (k_rollout_tab_sliced) would run;
  * "max_unroll", "block", "smem_pad", "tc_stagger", "host_ranges" select kernel / pipeline variants for measurements. */
 int carenv_set_option(void *handle, const char *name, int value);
 

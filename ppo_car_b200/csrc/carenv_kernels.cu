@@ -13,6 +13,9 @@
 //   k_gae       Buffer.calculate_advantages as a reverse scan, one thread per environment column.
 //   k_rollout_tab   launches of 4,096 environments or more: the same step with the denominators cross(e, d) read
 //               from a per-track shared-memory table (8 skewed, conflict-free copies), one 512-thread CTA per SM.
+//   k_rollout_tab_sliced   the same for launches of >= 75,776 environments and >= 4 steps, with an SM's env-steps cut
+//               into 16 equal per-warp intervals (jobs that straddle two warps are split in time): four warps per
+//               scheduler until the launch ends.
 //   k_rollout_multi / k_reset_multi / k_render   a track id per environment in one launch; headless rgb_array frames.
 //   csrc/policy_rollout.cuh (included below)   k_policy_rollout / k_policy_rollout_tc / _tc2 / _tc3: policy forward +
 //               sampling + env step + Buffer rows in one launch (CUDA cores / tcgen05 tensor cores, policy_core.cuh,

@@ -705,6 +705,32 @@ CE_HD void env_step(EnvState &s, int action, double reward_scale, const TrackPar
     }
 }
 
+// Work list of one warp ("slot") of k_rollout_tab_sliced (carenv_kernels.cu).  n_jobs jobs of n_steps steps each are
+// laid end to end and cut into n_slots equal intervals of `quota` warp-steps (McNaughton's wrap-around rule); slot s
+// owns [s * quota, (s + 1) * quota).  A job cut by a boundary is split IN TIME between the two slots: the slot that
+// owns the END of the job's stretch in the linear order runs the job's FIRST steps at the start of its list (item
+// `first_job`, steps [0, head_len)), the slot that owns the beginning of the stretch runs the job's LAST steps at the
+// end of its list (job last_full + 1, steps [n_steps - tail_len, n_steps)) — so the first part, started at time 0, has
+// finished when the second starts at time quota - tail_len >= n_steps - tail_len = head_len (needs n_jobs >= n_slots).
+// In between: whole jobs first_job + (head_len > 0) .. last_full.
+struct SliceItems { int first_job, head_len, last_full, tail_len; };
+CE_HD SliceItems slice_items(int n_jobs, int n_steps, int slot, int n_slots) {
+    const long long total = (long long)n_jobs * n_steps;
+    const long long quota = (total + n_slots - 1) / n_slots;
+    long long lo = (long long)slot * quota;
+    if (lo > total) lo = total;
+    long long hi = lo + quota;
+    if (hi > total) hi = total;
+    SliceItems r;
+    r.first_job = (int)(lo / n_steps);
+    const int off = (int)(lo - (long long)r.first_job * n_steps);
+    r.head_len = off > 0 ? n_steps - off : 0;
+    r.last_full = (int)(hi / n_steps) - 1;                   // last job that ends at or before hi
+    r.tail_len = (int)(hi - (long long)(r.last_full + 1) * n_steps);
+    if (lo >= hi) { r.head_len = 0; r.tail_len = 0; r.last_full = r.first_job - 1; }
+    return r;
+}
+
 // Observation of the start pose (what CarEnv.reset returns, lib/car_env.py:682-688), evaluated
 // with the literal float64 formulas; also tells whether the start pose already collides.
 CE_HD bool reset_observation(const TrackParams &P, const Tables &T, float obs[kObsDim]) {

@@ -417,18 +417,8 @@ k_rollout_tab_sliced(const __grid_constant__ TrackParams P, const Tables G, cons
     //   the job cut by lo (the previous warp holds its LAST steps): its first steps   [item first_job, steps 0 .. head_len)
     //   whole jobs                                                                    [first_job + has_head .. last_full]
     //   the job cut by hi (the next warp runs its first steps): its last steps        [item tail_job, steps n - tail_len .. n)
-    int first_job, head_len, last_full, tail_len;
-    {
-        const long long total = (long long)(job_hi - job_lo) * n_steps;
-        const long long quota = (total + n_slots - 1) / n_slots;                 // >= n_steps (the launcher checks)
-        const long long lo = min(total, (long long)slot * quota), hi = min(total, lo + quota);
-        first_job = (int)(lo / n_steps);
-        const int off = (int)(lo - (long long)first_job * n_steps);
-        head_len = off > 0 ? n_steps - off : 0;
-        last_full = (int)(hi / n_steps) - 1;                                      // last job that ends at or before hi
-        tail_len = (int)(hi - (long long)(last_full + 1) * n_steps);
-        if (lo >= hi) { head_len = 0; tail_len = 0; last_full = first_job - 1; }
-    }
+    const SliceItems items = slice_items(job_hi - job_lo, n_steps, slot, n_slots);   // carenv_core.cuh (tested on the host)
+    const int first_job = items.first_job, head_len = items.head_len, last_full = items.last_full, tail_len = items.tail_len;
     // (item bookkeeping in shared memory instead of registers was measured: fewer spills, 1.5 % slower)
     const int n_items = (last_full + 1 - first_job) + (tail_len > 0 ? 1 : 0);     // the head item is job first_job itself
     for (int it = 0; it < n_items; ++it) {

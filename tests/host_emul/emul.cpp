@@ -63,3 +63,9 @@ extern "C" int emul_heading_table(double angle, double *cos_sin_out /* [72][2] *
     for (int k = 0; k < kHeadings; ++k) { cos_sin_out[2 * k] = H.trig64[k].x; cos_sin_out[2 * k + 1] = H.trig64[k].y; }
     return 0;
 }
+
+// The per-warp work list of the time-sliced table kernel, exactly as the kernel computes it.
+extern "C" void emul_slice_items(int n_jobs, int n_steps, int slot, int n_slots, int *out4) {
+    const SliceItems r = slice_items(n_jobs, n_steps, slot, n_slots);
+    out4[0] = r.first_job; out4[1] = r.head_len; out4[2] = r.last_full; out4[3] = r.tail_len;
+}

@@ -239,3 +239,46 @@ def test_heading_table_equals_numpy_trigonometry(tracks_dir):
                 err = np.abs(tab[:, col] - ref)
                 # the argument itself is only known to half a unit in the last place of ~13 rad: a few 1e-15
                 assert err.max() <= 4.0e-15, (ang, turns, err.max())
+
+
+def test_time_slice_work_lists_cover_every_step_once_and_in_order():
+    """slice_items (carenv_core.cuh, what every warp of k_rollout_tab_sliced computes for itself): over all warps the
+    items cover every (job, step) exactly once; a job cut between two warps is split into first steps / last steps
+    with the first part scheduled before the second starts (the property the in-kernel flag only double-checks)."""
+    import ctypes as C
+
+    from tests.emul_util import lib
+
+    L = lib()
+    rng = np.random.default_rng(5)
+    cases = [(28, 256, 16), (27, 256, 16), (16, 4, 16), (222, 256, 16), (221, 1024, 16), (17, 5, 16), (16, 7, 16), (40, 1, 16)]
+    cases += [(int(rng.integers(16, 400)), int(rng.integers(1, 600)), 16) for _ in range(60)]
+    out = (C.c_int * 4)()
+    for n_jobs, n_steps, n_slots in cases:
+        total = n_jobs * n_steps
+        quota = -(-total // n_slots)
+        seen = np.zeros((n_jobs, n_steps), np.int32)
+        head_end, tail_start = {}, {}
+        for slot in range(n_slots):
+            L.emul_slice_items(n_jobs, n_steps, slot, n_slots, out)
+            first_job, head_len, last_full, tail_len = list(out)
+            clock = 0
+            job = first_job
+            if head_len > 0:
+                seen[job, :head_len] += 1
+                clock += head_len
+                head_end[job] = clock
+                job += 1
+            while job <= last_full:
+                seen[job] += 1
+                clock += n_steps
+                job += 1
+            if tail_len > 0:
+                tail_start[job] = clock
+                seen[job, n_steps - tail_len:] += 1
+                clock += tail_len
+            assert clock <= quota
+        assert np.all(seen == 1), (n_jobs, n_steps)
+        assert set(head_end) == set(tail_start)
+        for job in head_end:
+            assert head_end[job] <= tail_start[job], (n_jobs, n_steps, job)

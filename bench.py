@@ -31,13 +31,15 @@ such as 8 x 32 measure 2-18 % less, depending on the shard size).
             cores, one process per core, on a bounded sample; kind "reference".  The oracle port's rate
             is reported beside it (`port_value`).  Without oracle/_ref: the port, kind "port".
   configs   BASELINE.json's other configurations, measured after the timed region on rank 0:
-            config 2 (24 envs x 1024 steps), config 3 (65,536 envs x 1024 steps rollout + GAE) and, at
+            config 2 (24 envs x 1024 steps), config 3 (65,536 envs x 1024 steps rollout + GAE), the README
+            training run and the fused policy + env rollout at 1 M envs (the callers of the hot path) and, at
             --gpus 8, config 5 (PPO loop, 262,144 envs: fused rollout, GAE kernel, all minibatch updates of an
             epoch in one launch with the gradient all-reduce over NVLink peer memory inside the kernel)
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -300,6 +302,46 @@ def other_configs(dev, world):
                       "rollout_ms": ms_r, "rollout_env_steps_per_s": n * T / (ms_r * 1e-3), "gae_ms": ms_g,
                       "gae_gbs": n * T * 24 / (ms_g * 1e-3) / 1e9,
                       "env_steps_per_s": n * T / ((ms_r + ms_g) * 1e-3)}
+    del env, obs, rew, te, tr, val, adv, ret, a
+    # the callers of the hot path, reported, never fatal: the reference's README training run
+    # (24 envs x 1024 steps x 200 epochs, "about 35 minutes") and the fused policy + env rollout at the bench size
+    try:
+        import time
+
+        from ppo_car_b200 import train_ppo
+
+        targs = train_ppo.parse_args(["--track", TRACK, "--n-envs", "24", "--n-epochs", "200", "--fused-rollout",
+                                      "--fused-update"])
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(sys.stderr):         # the contract: ONE JSON line on stdout
+            hist = train_ppo.train(targs)
+        out["readme_training"] = {"workload": "PPO loop with the README hyper-parameters: big_track.json, 24 envs x 1024 "
+                                              "steps x 200 epochs (fused warp-per-environment rollout, one update "
+                                              "launch per epoch)", "wall_s": hist[-1]["wall_s"],   # the loop's own clock, as train.py logs it
+                                  "wall_with_setup_s": time.perf_counter() - t0,
+                                  "final_avg_reward": sum(h["avg_reward"] for h in hist[-10:]) / 10}
+        from ppo_car_b200.train_ppo import ActorCritic
+
+        torch.manual_seed(0)
+        n, T = 1_048_576, 16
+        net = ActorCritic(18, 9).to(dev)
+        packed = ppo_car_b200.pack_policy_weights_tc(net.actor, net.critic)
+        env = ppo_car_b200.VecCarEnv(n, track, device=dev, reward_scaling=0.1, float_flags=True, with_info=False)
+        buf = ppo_car_b200.Buffer((18,), T, n, dev)
+        cur = env.reset()[0].clone()
+        z1, z2, lv = torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.empty(n, device=dev)
+        step = [0]
+
+        def fused():
+            ppo_car_b200.fused_rollout(env, packed, buf, cur, z1, z2, seed=1, step0=step[0], last_val=lv)
+            step[0] += T
+
+        ms_f = timed(fused, 3)
+        out["fused_rollout"] = {"workload": "policy forward (18-256-9 / 18-256-1, tcgen05) + sampling + env step + Buffer "
+                                            "rows in one launch, 1,048,576 envs x 16 steps (k_policy_rollout_tc3)",
+                                "ms": ms_f, "env_steps_per_s": n * T / (ms_f * 1e-3)}
+    except Exception as exc:
+        out["callers_error"] = repr(exc)[:300]
     return out
 
 
@@ -312,7 +354,8 @@ def config5(args):
 
     targs = train_ppo.parse_args(["--track", TRACK, "--n-envs", "262144", "--n-epochs", "6", "--fused-rollout",
                                   "--fused-update"])
-    hist = train_ppo.train(targs)
+    with contextlib.redirect_stdout(sys.stderr):             # the contract: ONE JSON line on stdout
+        hist = train_ppo.train(targs)
     per_epoch = [hist[i]["wall_s"] - hist[i - 1]["wall_s"] for i in range(1, len(hist))]
     ms = 1e3 * sorted(per_epoch)[len(per_epoch) // 2]
     return {"workload": "PPO loop, README hyper-parameters, 262,144 envs over 8 GPUs x 1024 steps per epoch: fused "
